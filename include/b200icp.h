@@ -1,0 +1,178 @@
+/* b200icp.h -- C ABI of the B200-native ICP correspondence-and-alignment engine.
+ *
+ * This is the drop-in boundary for ONE path of JMUWRobotics/3DTK: per-iteration nearest-neighbour
+ * correspondence search + distance rejection + covariance / residual accumulation + 6-DoF solve.
+ * Every entry point names the reference interface it replaces (paths relative to the 3DTK tree,
+ * commit 5b570686).  The reference-side C++ adapter (class GpuSearchTree : public SearchTree,
+ * class icp6D_gpu : public icp6D) that binds these symbols is shown in INTEGRATION.md and shipped
+ * in 3dtk_b200/host/.
+ *
+ * Conventions (identical to the reference, include/slam6d/globals.icc:298-321, :1454-1490):
+ *   - 4x4 matrices are double[16] in column-major OpenGL order, translation in [12..14];
+ *   - points / normals are fp64 AoS, 3 doubles per element (DataXYZ / DataNormal);
+ *   - all functions return 0 on success, a negative B200ICP_E* code otherwise, never throw;
+ *     b200icp_last_error() gives the message of the calling thread's last failure;
+ *   - indices returned refer to the caller's original point order (row of the uploaded array).
+ *   - The library needs a CUDA device (sm_100a).  There is NO CPU fallback: without a usable GPU
+ *     b200icp_create() fails with B200ICP_ENODEV and nothing else can be called.
+ */
+#ifndef B200ICP_H_
+#define B200ICP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ICP_OK 0
+#define B200ICP_EINVAL (-1)  /* bad argument                                             */
+#define B200ICP_ENODEV (-2)  /* no CUDA device / wrong architecture                       */
+#define B200ICP_ECUDA (-3)   /* CUDA runtime error (message in b200icp_last_error)        */
+#define B200ICP_ENOMEM (-4)  /* host or device allocation failed                          */
+#define B200ICP_EEMPTY (-5)  /* zero points (reference: kdTreeImpl.h:86-88 throws)        */
+#define B200ICP_ESTATE (-6)  /* object used in a state that does not allow the call       */
+
+/* icp6Dminimizer::getAlgorithmID() values (include/slam6d/icp6D{quat,svd,apx,napx}.h) */
+#define B200ICP_ALGO_QUAT 1
+#define B200ICP_ALGO_SVD 2
+#define B200ICP_ALGO_APX 6
+#define B200ICP_ALGO_NAPX 10
+
+/* PairingMode (include/slam6d/pairingMode.h:4-8); mode 1 (along-normal) is not on the path */
+#define B200ICP_CLOSEST_POINT 0
+#define B200ICP_CLOSEST_PLANE_SIMPLE 2
+
+typedef struct b200icp_ctx b200icp_ctx;   /* one per host thread / CUDA stream            */
+typedef struct b200icp_scan b200icp_scan; /* device-resident scan: points + search grid   */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int b200icp_create(int device, b200icp_ctx** out);
+void b200icp_destroy(b200icp_ctx* ctx);
+/* Run all subsequent work of this context on `cuda_stream` (a cudaStream_t; NULL = own stream). */
+int b200icp_set_stream(b200icp_ctx* ctx, void* cuda_stream);
+int b200icp_synchronize(b200icp_ctx* ctx);
+const char* b200icp_last_error(void);
+/* Version / build info string ("b200icp <ver> sm_100a ..."). */
+const char* b200icp_version(void);
+
+/* ---- scans ---------------------------------------------------------------------------------
+ * Replaces: Scan::createSearchTree / BasicScan::createSearchTreePrivate (src/slam6d/scan.cc:285-306,
+ * basicScan.cc:702-728) + KDtree::KDtree (src/slam6d/kd.cc:46-49).  `xyz` is the scan's
+ * "xyz reduced original" array (points in the frame the tree is built in); `normals` (may be NULL)
+ * its "normal reduced".  The arrays are copied; the caller keeps ownership.
+ * cell_edge <= 0 picks the grid cell edge from the point density; max_dist_hint (> 0) is the search
+ * radius the scan will mostly be queried with (icp6D's max_dist_match), used only for that choice.
+ * A scan can act as model (Source) and as data (Target) of a match.
+ * transMat / dalignxf start as identity (basicScan.cc:293); see b200icp_scan_set_pose. */
+int b200icp_scan_create(b200icp_ctx* ctx, const double* xyz, const double* normals, size_t n,
+                        double cell_edge, double max_dist_hint, b200icp_scan** out);
+/* Same, but xyz / normals are DEVICE pointers (fp64 AoS) already resident in HBM. */
+int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const double* d_normals,
+                               size_t n, double cell_edge, double max_dist_hint,
+                               b200icp_scan** out);
+void b200icp_scan_destroy(b200icp_ctx* ctx, b200icp_scan* scan);
+size_t b200icp_scan_size(const b200icp_scan* scan);
+/* grid facts: dims[3], cell edge, number of cells, occupied cells */
+int b200icp_scan_grid_info(const b200icp_scan* scan, int dims[3], double* cell_edge,
+                           uint64_t* n_cells, uint64_t* n_occupied);
+/* Scan::transMat / Scan::dalignxf (scan.cc:878-898).  Either pointer may be NULL. */
+int b200icp_scan_get_pose(const b200icp_scan* scan, double transMat[16], double dalignxf[16]);
+int b200icp_scan_set_pose(b200icp_scan* scan, const double transMat[16], const double dalignxf[16]);
+/* Current "xyz reduced" (= dalignxf * original) and "normal reduced", original row order;
+ * what Scan::transformReduced (scan.cc:851-875) leaves in the arrays.  nrm_out may be NULL. */
+int b200icp_scan_download(b200icp_ctx* ctx, const b200icp_scan* scan, double* xyz_out,
+                          double* nrm_out);
+
+/* ---- API-compatible search path --------------------------------------------------------------
+ * Replaces: KDtree::FindClosest (src/slam6d/kd.cc:78-87; include/slam6d/searchTree.h:81).
+ * Exact fp64 nearest neighbour with the k-d tree's strict rule d^2 < maxdist2
+ * (kdTreeImpl.h:353; testing/kdtree/kdtree.cc:20-35).  *idx_out = row of the model point, or -1.
+ * Exact-distance ties resolve to the lowest row (the k-d tree's choice depends on build order). */
+int b200icp_find_closest(b200icp_ctx* ctx, const b200icp_scan* model, const double p[3],
+                         double maxdist2, int64_t* idx_out);
+
+/* Replaces: the batch loop SearchTree::getPtPairs (src/slam6d/searchTree.cc:92-188) minus PtPair
+ * materialisation.  For i in [0,n): t = q_xyz[i]; s = inv(source_alignxf) * t; NN of s in the model
+ * grid within maxdist2; idx_out[i] = model row or -1; d2_out[i] (optional) = squared distance in the
+ * tree frame.  sums_out (optional, 8 doubles, ASSIGNED): {npairs, sum |p1-p2|^2, centroid_m[3] (sum,
+ * not divided), centroid_d[3] (sum)} exactly as getPtPairs accumulates them, including the
+ * CLOSEST_PLANE_SIMPLE projection (searchTree.cc:149-162) when pairing_mode == 2 (q_nrm required).
+ * All pointers are HOST pointers; the H2D / D2H copies are part of the call. */
+int b200icp_nn_batch(b200icp_ctx* ctx, const b200icp_scan* model, const double* q_xyz,
+                     const double* q_nrm, size_t n, const double source_alignxf[16],
+                     double maxdist2, int pairing_mode, int32_t* idx_out, double* d2_out,
+                     double sums_out[8]);
+/* Same with DEVICE pointers (q_xyz, q_nrm, idx_out, d2_out on device; sums_out on host). */
+int b200icp_nn_batch_device(b200icp_ctx* ctx, const b200icp_scan* model, const double* d_q_xyz,
+                            const double* d_q_nrm, size_t n, const double source_alignxf[16],
+                            double maxdist2, int pairing_mode, int32_t* d_idx_out,
+                            double* d_d2_out, double sums_out[8]);
+
+/* ---- 6-DoF solve from pair moments (host; also what the device solve kernel runs) -------------
+ * Replaces: icp6D_QUAT/SVD/APX/NAPX::Align (src/slam6d/icp6Dquat.cc:38-144, icp6Dsvd.cc:38-158,
+ * icp6Dapx.cc:35-133, icp6Dnapx.cc:34-149) operating on explicit pairs: p1 = model-side point,
+ * p2 = data-side point, nrm = per-pair unit normal (NAPX only, else NULL).  centroid_m/centroid_d
+ * as passed by icp6D::match.  Returns the RMS the reference returns through *rms_out
+ * (-1.0 when the Cholesky factorisation fails, icp6Dapx.cc:97-100).  Pure host arithmetic over
+ * the moment sums -- used by the adapter's Align override and by CPU-side tests. */
+int b200icp_align_pairs(int algo, size_t n, const double* p1, const double* p2, const double* nrm,
+                        const double centroid_m[3], const double centroid_d[3],
+                        double alignxf[16], double* rms_out);
+
+/* ---- fused match -------------------------------------------------------------------------------
+ * Replaces: icp6D::match (src/slam6d/icp6D.cc:104-285) -- Scan::getPtPairs + Align + Scan::transform
+ * per iteration, convergence test icp6D.cc:266-268 -- entirely on the device. */
+typedef struct b200icp_match_params {
+  int algo;               /* B200ICP_ALGO_*                                                  */
+  int pairing_mode;       /* B200ICP_CLOSEST_POINT | B200ICP_CLOSEST_PLANE_SIMPLE            */
+  double max_dist_match;  /* NOT squared (icp6D ctor squares it, icp6D.cc:80)                */
+  int max_num_iterations; /* icp6D::max_num_iterations                                       */
+  double epsilon_icp;     /* icp6D::epsilonICP                                               */
+  int rnd;                /* <=1: every point; >1: deterministic 1/rnd subsample             */
+  int exact;              /* 1: fp32 filter + fp64 verified NN (default); 0: fp32 decisions  */
+  int profile;            /* 1: record per-launch CUDA-event timings (b200icp_match_profile) */
+  int napx_weighted;      /* 0: B as shipped (icp6Dnapx.cc:69-74); 1: least-squares B += d*[c;n] */
+  int reserved[3];
+} b200icp_match_params;
+
+typedef struct b200icp_match_result {
+  int iterations;       /* value icp6D::match returns (loop index at exit)                   */
+  int iterations_run;   /* iterations that produced a transform (entries in rms / npairs)    */
+  double rms_last;
+  uint64_t npairs_last;
+  uint64_t queries;     /* data points searched per iteration                                */
+  double nn_kernel_ms;  /* profile=1: mean device time of one correspondence kernel launch   */
+  double solve_kernel_ms;
+  uint32_t kernel_launches; /* kernels launched by this call                                 */
+  uint32_t stage2_queries_last; /* queries that needed the wide (ring) search, last iteration */
+} b200icp_match_result;
+
+/* model->dalignxf is used as Source->dalignxf; data's transMat / dalignxf are updated in place
+ * (b200icp_scan_get_pose).  rms_per_iter / npairs_per_iter (optional) receive
+ * max_num_iterations entries at most. */
+int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* data,
+                  const b200icp_match_params* params, double* rms_per_iter,
+                  uint64_t* npairs_per_iter, b200icp_match_result* result);
+
+/* ---- normals --------------------------------------------------------------------------------
+ * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):
+ * exact k nearest neighbours (the point itself included), PCA, smallest-eigenvalue eigenvector,
+ * flipped so that n . (p - rPos) >= 0, unit length.  Host pointers. */
+int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, const double rPos[3],
+                        double* normals_out);
+
+/* ---- synthetic inputs (host only, no GPU needed) -------------------------
+ * scene(seed, n): indoor box scene, area-proportional surface sampling, N(0, noise^2) per coordinate. */
+int b200icp_synth_scene(uint64_t seed, size_t n, double noise_sigma, double* xyz_out);
+/* EulerToMatrix4 (globals.icc:501-531) -- exported so every binding builds poses identically. */
+void b200icp_euler_to_matrix4(const double rPos[3], const double rPosTheta[3], double out[16]);
+int b200icp_m4inv(const double in[16], double out[16]);
+void b200icp_mmult(const double a[16], const double b[16], double out[16]);
+void b200icp_transform_points(const double xf[16], double* xyz, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ICP_H_ */
