@@ -1,0 +1,301 @@
+"""3dtk_b200 -- ctypes binding over the C ABI in include/b200icp.h (lib/libb200icp.so).
+
+The package name starts with a digit, so import it with
+    icp = importlib.import_module("3dtk_b200")
+This binding is harness glue for tests/ and bench.py; the product is the shared library.  There is no
+CPU fallback anywhere: if the library is missing the import raises, and without a CUDA device
+`Context()` raises `B200ICPError` (ENODEV).
+
+Names mirror the reference's interface for this path (3DTK, paths relative to its tree):
+  Scan  <-> Scan + its SearchTree   (src/slam6d/scan.cc:285-306, basicScan.cc:702-728)
+  Scan.find_closest / get_pt_pairs  <-> SearchTree::FindClosest / getPtPairs (searchTree.h:81-112)
+  icp6D.match                        <-> icp6D::match (include/slam6d/icp6D.h:51-53)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200icp.so")
+
+ALGO_QUAT, ALGO_SVD, ALGO_APX, ALGO_NAPX = 1, 2, 6, 10
+CLOSEST_POINT, CLOSEST_PLANE_SIMPLE = 0, 2
+
+E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "EEMPTY", -6: "ESTATE"}
+
+
+class B200ICPError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200icp %s (%d): %s" % (E_NAMES.get(code, "?"), code, msg))
+        self.code = code
+
+
+class MatchParams(C.Structure):
+    _fields_ = [("algo", C.c_int), ("pairing_mode", C.c_int), ("max_dist_match", C.c_double),
+                ("max_num_iterations", C.c_int), ("epsilon_icp", C.c_double), ("rnd", C.c_int),
+                ("exact", C.c_int), ("profile", C.c_int), ("napx_weighted", C.c_int),
+                ("reserved", C.c_int * 3)]
+
+
+class MatchResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("iterations_run", C.c_int), ("rms_last", C.c_double),
+                ("npairs_last", C.c_uint64), ("queries", C.c_uint64), ("nn_kernel_ms", C.c_double),
+                ("solve_kernel_ms", C.c_double), ("kernel_launches", C.c_uint32),
+                ("stage2_queries_last", C.c_uint32)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "3dtk_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no pure-Python or CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, sz, i32, f64 = C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double
+    sig = {
+        "b200icp_create": (i32, [i32, C.POINTER(vp)]),
+        "b200icp_destroy": (None, [vp]),
+        "b200icp_set_stream": (i32, [vp, vp]),
+        "b200icp_synchronize": (i32, [vp]),
+        "b200icp_last_error": (C.c_char_p, []),
+        "b200icp_version": (C.c_char_p, []),
+        "b200icp_scan_create": (i32, [vp, dp, dp, sz, f64, f64, C.POINTER(vp)]),
+        "b200icp_scan_create_device": (i32, [vp, dp, dp, sz, f64, f64, C.POINTER(vp)]),
+        "b200icp_scan_destroy": (None, [vp, vp]),
+        "b200icp_scan_size": (sz, [vp]),
+        "b200icp_scan_grid_info": (i32, [vp, C.POINTER(i32 * 3), C.POINTER(f64), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint64)]),
+        "b200icp_scan_get_pose": (i32, [vp, dp, dp]),
+        "b200icp_scan_set_pose": (i32, [vp, dp, dp]),
+        "b200icp_scan_download": (i32, [vp, vp, dp, dp]),
+        "b200icp_find_closest": (i32, [vp, vp, dp, f64, C.POINTER(C.c_int64)]),
+        "b200icp_nn_batch": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
+        "b200icp_nn_batch_device": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
+        "b200icp_align_pairs": (i32, [i32, sz, dp, dp, dp, dp, dp, dp, C.POINTER(f64)]),
+        "b200icp_match": (i32, [vp, vp, vp, C.POINTER(MatchParams), dp, dp, C.POINTER(MatchResult)]),
+        "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
+        "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
+        "b200icp_euler_to_matrix4": (None, [dp, dp, dp]),
+        "b200icp_m4inv": (i32, [dp, dp]),
+        "b200icp_mmult": (None, [dp, dp, dp]),
+        "b200icp_transform_points": (None, [dp, dp, sz]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)   # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sig)
+
+
+lib, EXPORTED = _load()
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200ICPError(rc, lib.b200icp_last_error().decode())
+
+
+def _f64(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_last is not None and (a.ndim == 0 or a.shape[-1] != shape_last):
+        raise ValueError("expected trailing dimension %d" % shape_last)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+# ---- host-only helpers (no GPU) -----------------------------------------------------------------
+def synth_scene(geom_seed, sample_seed, n, noise_sigma=0.5):
+    out = np.empty((n, 3), dtype=np.float64)
+    _check(lib.b200icp_synth_scene(geom_seed, sample_seed, n, noise_sigma, _ptr(out)))
+    return out
+
+
+def euler_to_matrix4(rpos, rpostheta):
+    m = np.empty(16)
+    lib.b200icp_euler_to_matrix4(_ptr(_f64(rpos)), _ptr(_f64(rpostheta)), _ptr(m))
+    return m
+
+
+def m4inv(m):
+    out = np.empty(16)
+    ok = lib.b200icp_m4inv(_ptr(_f64(m).reshape(16)), _ptr(out))
+    return out, ok
+
+
+def mmult(a, b):
+    out = np.empty(16)
+    lib.b200icp_mmult(_ptr(_f64(a).reshape(16)), _ptr(_f64(b).reshape(16)), _ptr(out))
+    return out
+
+
+def transform_points(xf, xyz):
+    out = _f64(xyz, 3).copy()
+    lib.b200icp_transform_points(_ptr(_f64(xf).reshape(16)), _ptr(out), out.shape[0])
+    return out
+
+
+def align_pairs(algo, p1, p2, nrm=None, centroid_m=None, centroid_d=None):
+    """icp6Dminimizer::Align on an explicit pair list (host arithmetic). -> (alignxf[16], rms)"""
+    p1, p2 = _f64(p1, 3), _f64(p2, 3)
+    nrm = None if nrm is None else _f64(nrm, 3)
+    cm = _f64(p1.mean(0) if centroid_m is None else centroid_m)
+    cd = _f64(p2.mean(0) if centroid_d is None else centroid_d)
+    xf, rms = np.empty(16), C.c_double(0)
+    _check(lib.b200icp_align_pairs(algo, p1.shape[0], _ptr(p1), _ptr(p2), _ptr(nrm), _ptr(cm), _ptr(cd),
+                                   _ptr(xf), C.byref(rms)))
+    return xf, rms.value
+
+
+# ---- device objects ----------------------------------------------------------------------------
+class Context:
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        _check(lib.b200icp_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, cuda_stream):
+        _check(lib.b200icp_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _check(lib.b200icp_synchronize(self._h))
+
+    def close(self):
+        if self._h:
+            lib.b200icp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scan:
+    """A scan resident on the device with its search grid (model and/or data role)."""
+
+    def __init__(self, ctx, xyz=None, normals=None, cell_edge=0.0, max_dist_hint=0.0,
+                 device_ptrs=None, n=None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if device_ptrs is not None:
+            dx, dn = device_ptrs
+            _check(lib.b200icp_scan_create_device(ctx._h, C.c_void_p(dx), C.c_void_p(dn) if dn else None,
+                                                  n, cell_edge, max_dist_hint, C.byref(h)))
+        else:
+            xyz = _f64(xyz, 3)
+            normals = None if normals is None else _f64(normals, 3)
+            _check(lib.b200icp_scan_create(ctx._h, _ptr(xyz), _ptr(normals), xyz.shape[0], cell_edge,
+                                           max_dist_hint, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_host_pointers(cls, ctx, xyz_ptr, nrm_ptr, n, cell_edge=0.0, max_dist_hint=0.0):
+        """Raw host pointers (e.g. pinned torch tensors): the e2e path of bench.py."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(lib.b200icp_scan_create(ctx._h, C.c_void_p(xyz_ptr), C.c_void_p(nrm_ptr) if nrm_ptr else None,
+                                       n, cell_edge, max_dist_hint, C.byref(h)))
+        self._h = h
+        return self
+
+    def __len__(self):
+        return lib.b200icp_scan_size(self._h)
+
+    def grid_info(self):
+        dims, h, nc, no = (C.c_int * 3)(), C.c_double(), C.c_uint64(), C.c_uint64()
+        _check(lib.b200icp_scan_grid_info(self._h, C.byref(dims), C.byref(h), C.byref(nc), C.byref(no)))
+        return {"dims": tuple(dims), "cell_edge": h.value, "n_cells": nc.value, "n_occupied": no.value}
+
+    def get_pose(self):
+        t, d = np.empty(16), np.empty(16)
+        _check(lib.b200icp_scan_get_pose(self._h, _ptr(t), _ptr(d)))
+        return t, d
+
+    def set_pose(self, transmat=None, dalignxf=None):
+        t = None if transmat is None else _f64(transmat).reshape(16)
+        d = None if dalignxf is None else _f64(dalignxf).reshape(16)
+        _check(lib.b200icp_scan_set_pose(self._h, _ptr(t), _ptr(d)))
+
+    def download(self, with_normals=False):
+        n = len(self)
+        xyz = np.empty((n, 3))
+        nrm = np.empty((n, 3)) if with_normals else None
+        _check(lib.b200icp_scan_download(self.ctx._h, self._h, _ptr(xyz), _ptr(nrm)))
+        return (xyz, nrm) if with_normals else xyz
+
+    # SearchTree::FindClosest
+    def find_closest(self, p, maxdist2):
+        p = _f64(p)
+        idx = C.c_int64(-1)
+        _check(lib.b200icp_find_closest(self.ctx._h, self._h, _ptr(p), maxdist2, C.byref(idx)))
+        return idx.value
+
+    # SearchTree::getPtPairs (index form)
+    def nn_batch(self, q_xyz, maxdist2, source_alignxf=None, q_nrm=None, pairing_mode=CLOSEST_POINT,
+                 want_d2=True):
+        q = _f64(q_xyz, 3)
+        nq = q.shape[0]
+        nrm = None if q_nrm is None else _f64(q_nrm, 3)
+        xf = None if source_alignxf is None else _f64(source_alignxf).reshape(16)
+        idx = np.empty(nq, dtype=np.int32)
+        d2 = np.empty(nq) if want_d2 else None
+        sums = np.zeros(8)
+        _check(lib.b200icp_nn_batch(self.ctx._h, self._h, _ptr(q), _ptr(nrm), nq, _ptr(xf), maxdist2,
+                                    pairing_mode, _ptr(idx), _ptr(d2), _ptr(sums)))
+        return idx, d2, sums
+
+    def destroy(self):
+        if getattr(self, "_h", None):
+            lib.b200icp_scan_destroy(self.ctx._h if self.ctx._h else None, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class icp6D:
+    """Mirror of the reference's icp6D (include/slam6d/icp6D.h:27-156) for the accelerated path."""
+
+    def __init__(self, ctx, algo=ALGO_QUAT, max_dist_match=25.0, max_num_iterations=50,
+                 epsilon_icp=1e-7, rnd=1, exact=True, napx_weighted=False, profile=False):
+        if max_dist_match < 0.0:
+            raise ValueError("ERROR [ICP6D]: first parameter (max_dist_match) has to be >= 0")
+        if max_num_iterations < 0:
+            raise ValueError("ERROR [ICP6D]: second parameter (max_num_iterations) has to be >= 0")
+        self.ctx = ctx
+        self.params = MatchParams(algo=algo, pairing_mode=CLOSEST_POINT, max_dist_match=max_dist_match,
+                                  max_num_iterations=max_num_iterations, epsilon_icp=epsilon_icp, rnd=rnd,
+                                  exact=1 if exact else 0, profile=1 if profile else 0,
+                                  napx_weighted=1 if napx_weighted else 0)
+
+    def match(self, previous_scan, current_scan, pairing_mode=CLOSEST_POINT):
+        """-> dict(iterations, rms[], npairs[], result struct).  Updates current_scan's pose."""
+        p = self.params
+        p.pairing_mode = pairing_mode
+        n = max(p.max_num_iterations, 1)
+        rms = np.zeros(n)
+        npairs = np.zeros(n, dtype=np.uint64)
+        res = MatchResult()
+        _check(lib.b200icp_match(self.ctx._h, previous_scan._h, current_scan._h, C.byref(p), _ptr(rms),
+                                 _ptr(npairs), C.byref(res)))
+        k = res.iterations_run
+        return {"iterations": res.iterations, "iterations_run": k, "rms": rms[:k].copy(),
+                "npairs": npairs[:k].copy(), "result": res}
+
+
+def normals_knn(ctx, xyz, k, rpos):
+    xyz = _f64(xyz, 3)
+    out = np.empty_like(xyz)
+    _check(lib.b200icp_normals_knn(ctx._h, _ptr(xyz), xyz.shape[0], k, _ptr(_f64(rpos)), _ptr(out)))
+    return out

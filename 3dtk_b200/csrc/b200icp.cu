@@ -1,0 +1,698 @@
+// b200icp.cu -- C ABI (include/b200icp.h) over the sm_100a kernels.  One translation unit.
+//
+// Host orchestration only: buffer ownership, grid-build driver, the launch loop of the fused match.
+// All numerics run in the kernels of grid_build.cuh / nn_search.cuh / icp_kernels.cuh (device) or
+// solve.h (the O(1) solve, shared by device and host).
+#include "../../include/b200icp.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "grid_build.cuh"
+#include "icp_kernels.cuh"
+#include "normals.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(_e == cudaErrorMemoryAllocation ? B200ICP_ENOMEM : B200ICP_ECUDA,          \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  cudaError_t alloc(size_t n) {
+    release();
+    count = n;
+    if (n == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, n * sizeof(T));
+  }
+  cudaError_t ensure(size_t n) { return n <= count && p ? cudaSuccess : alloc(n); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    count = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+constexpr int kMaxProfileEvents = 4096;
+constexpr int kMaxBlocksPerSm = 8;  // partial-sum workspace is sized sm_count * kMaxBlocksPerSm
+
+}  // namespace
+
+struct b200icp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t own = nullptr;
+  // workspaces
+  DevBuf<double> partials;          // [max_blocks][NS_MAX]
+  DevBuf<IterState> d_state;
+  IterState* h_state = nullptr;     // pinned, 2 slots (speculative chunk polling)
+  DevBuf<double> rms_log;
+  DevBuf<unsigned long long> npairs_log;
+  DevBuf<unsigned> stage2_counter;
+  DevBuf<double> d_small;           // 64 doubles of scratch (transforms for API kernels)
+  double* h_small = nullptr;        // pinned 64 doubles
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int blocks_per_sm_batch = 0;
+};
+
+struct b200icp_scan {
+  size_t n = 0;
+  bool has_normals = false;
+  GridDev g;                     // device pointers into the buffers below
+  DevBuf<uint32_t> cell_start;
+  DevBuf<float4> p32;
+  DevBuf<double4> p64;
+  DevBuf<double4> nrm;
+  DevBuf<uint32_t> perm;
+  uint64_t n_cells = 0, n_occupied = 0;
+  double transMat[16];
+  double dalignxf[16];
+  double nmat[9];                // cumulative normal map (see IterState::Nm)
+};
+
+namespace {
+
+double cells_for(const double ext[3], double h, int dims[3]) {
+  double total = 1.0;
+  for (int k = 0; k < 3; ++k) {
+    double d = std::floor(ext[k] / h) + 1.0;
+    if (d > 2.0e9) d = 2.0e9;
+    dims[k] = (int)d;
+    total *= d;
+  }
+  return total;
+}
+
+template <bool NAPX, bool PLANE, bool EXACT>
+void launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const b200icp_scan* data,
+                 double maxdist2, int rnd, int* grid_out) {
+  auto kern = icp_iter_kernel<NAPX, PLANE, EXACT>;
+  if (ctx->blocks_per_sm[variant] == 0) {
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kBlock, 0);
+    ctx->blocks_per_sm[variant] = std::max(b, 1);
+  }
+  const uint32_t nd = (uint32_t)data->n;
+  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  const int grid = (int)std::min<uint32_t>(
+      ntiles, (uint32_t)(ctx->sm_count * std::min(ctx->blocks_per_sm[variant], kMaxBlocksPerSm)));
+  *grid_out = grid;
+  kern<<<grid, kBlock, 0, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p,
+                                         maxdist2, rnd, ctx->partials.p, ctx->stage2_counter.p);
+}
+
+int launch_iter_dispatch(b200icp_ctx* ctx, bool napx, bool plane, bool exact,
+                         const b200icp_scan* model, const b200icp_scan* data, double maxdist2,
+                         int rnd, int* grid_out) {
+  const int v = (napx ? 4 : 0) | (plane ? 2 : 0) | (exact ? 1 : 0);
+  switch (v) {
+    case 0: launch_iter<false, false, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 1: launch_iter<false, false, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 2: launch_iter<false, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 3: launch_iter<false, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 6: launch_iter<true, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 7: launch_iter<true, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+int max_iter_grid(const b200icp_ctx* ctx) { return ctx->sm_count * kMaxBlocksPerSm; }
+
+}  // namespace
+
+extern "C" {
+
+const char* b200icp_last_error(void) { return g_last_error.c_str(); }
+
+const char* b200icp_version(void) {
+  return "b200icp 0.1 (sm_100a; exact fp64-verified grid NN; fused match; no CPU fallback)";
+}
+
+int b200icp_create(int device, b200icp_ctx** out) {
+  if (!out) return fail(B200ICP_EINVAL, "b200icp_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(B200ICP_ENODEV, std::string("b200icp_create: no CUDA device (") +
+                                    cudaGetErrorString(e) + "); this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail(B200ICP_EINVAL, "b200icp_create: bad device index");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(B200ICP_ENODEV, std::string("b200icp_create: device '") + prop.name +
+                                    "' is not sm_100; kernels are built for sm_100a only");
+  CU_TRY(cudaSetDevice(device));
+  b200icp_ctx* ctx = new b200icp_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ctx; return fail(B200ICP_ECUDA, cudaGetErrorString(e)); }
+  ctx->stream = ctx->own;
+  ctx->own_stream = true;
+  bool ok = ctx->partials.alloc((size_t)max_iter_grid(ctx) * NS_MAX) == cudaSuccess &&
+            ctx->d_state.alloc(1) == cudaSuccess && ctx->stage2_counter.alloc(4) == cudaSuccess &&
+            ctx->d_small.alloc(64) == cudaSuccess &&
+            cudaMallocHost((void**)&ctx->h_state, 2 * sizeof(IterState)) == cudaSuccess &&
+            cudaMallocHost((void**)&ctx->h_small, 64 * sizeof(double)) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->poll_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->poll_ev[1], cudaEventDisableTiming) == cudaSuccess &&
+            cudaMemsetAsync(ctx->stage2_counter.p, 0, 4 * sizeof(unsigned), ctx->stream) == cudaSuccess;
+  if (!ok) {
+    std::string msg = cudaGetErrorString(cudaGetLastError());
+    b200icp_destroy(ctx);
+    return fail(B200ICP_ENOMEM, "b200icp_create: workspace allocation failed: " + msg);
+  }
+  *out = ctx;
+  return B200ICP_OK;
+}
+
+void b200icp_destroy(b200icp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->poll_ev[i]) cudaEventDestroy(ctx->poll_ev[i]);
+  if (ctx->h_state) cudaFreeHost(ctx->h_state);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  ctx->partials.release();
+  ctx->d_state.release();
+  ctx->rms_log.release();
+  ctx->npairs_log.release();
+  ctx->stage2_counter.release();
+  ctx->d_small.release();
+  if (ctx->own) cudaStreamDestroy(ctx->own);
+  delete ctx;
+}
+
+int b200icp_set_stream(b200icp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+  else { ctx->stream = ctx->own; ctx->own_stream = true; }
+  return B200ICP_OK;
+}
+
+int b200icp_synchronize(b200icp_ctx* ctx) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200ICP_OK;
+}
+
+// --------------------------------------------------------------------------------------- scans
+int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const double* d_normals,
+                               size_t n, double cell_edge, double max_dist_hint,
+                               b200icp_scan** out) {
+  if (!ctx || !out) return fail(B200ICP_EINVAL, "scan_create: NULL argument");
+  *out = nullptr;
+  if (n == 0) return fail(B200ICP_EEMPTY, "scan_create: cannot build a search grid over zero points");
+  if (!d_xyz) return fail(B200ICP_EINVAL, "scan_create: xyz is NULL");
+  if (n >= (1ull << 31)) return fail(B200ICP_EINVAL, "scan_create: more than 2^31-1 points");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+
+  // ---- bbox
+  const int bb_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4);
+  DevBuf<double> bb_part, bb_out;
+  CU_TRY(bb_part.alloc((size_t)bb_blocks * 6));
+  CU_TRY(bb_out.alloc(6));
+  bbox_partial_kernel<<<bb_blocks, 256, 0, st>>>(d_xyz, n, bb_part.p);
+  bbox_final_kernel<<<1, 32, 0, st>>>(bb_part.p, bb_blocks, bb_out.p);
+  double bb[6];
+  CU_TRY(cudaMemcpyAsync(bb, bb_out.p, sizeof bb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  for (int k = 0; k < 6; ++k)
+    if (!std::isfinite(bb[k])) return fail(B200ICP_EINVAL, "scan_create: non-finite coordinate in xyz");
+  double ext[3] = {bb[3] - bb[0], bb[4] - bb[1], bb[5] - bb[2]};
+  const double max_ext = std::max(ext[0], std::max(ext[1], ext[2]));
+
+  // ---- cell edge
+  int dims[3];
+  double h_floor = std::max(max_ext * 1e-6, 1e-9);  // smallest edge whose dense table fits the cap
+  while (cells_for(ext, h_floor, dims) > (double)kCellCap) h_floor *= 1.08;
+  const char* env_ppc = getenv("B200ICP_TARGET_PPC");
+  const double target_ppc = env_ppc ? std::max(atof(env_ppc), 0.25) : 3.0;
+  DevBuf<uint32_t> counts;
+  DevBuf<unsigned long long> occ_dev;
+  CU_TRY(occ_dev.alloc(1));
+  GridShape gs;
+  unsigned long long occ = 0;
+  auto bin_points = [&](double h, uint32_t* keys, uint32_t* vals) -> cudaError_t {
+    const double nc = cells_for(ext, h, dims);
+    gs.h = h; gs.inv_h = 1.0 / h;
+    gs.nx = dims[0]; gs.ny = dims[1]; gs.nz = dims[2];
+    for (int k = 0; k < 3; ++k) gs.g0[k] = bb[k];
+    cudaError_t e = counts.ensure((size_t)nc + 1);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(counts.p, 0, ((size_t)nc + 1) * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyz, n, gs, keys, vals, counts.p);
+    e = cudaMemsetAsync(occ_dev.p, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    count_occupied_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(counts.p, (size_t)nc, occ_dev.p);
+    e = cudaMemcpyAsync(&occ, occ_dev.p, sizeof occ, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+  };
+  double h;
+  if (cell_edge > 0.0) {
+    h = std::max(cell_edge, h_floor);
+  } else {
+    // density-driven choice: aim at `target_ppc` points per OCCUPIED cell (surface-like data: ppc ~ h^2)
+    double vol = 1.0;
+    for (int k = 0; k < 3; ++k) vol *= std::max(ext[k], max_ext * 1e-3 + 1e-9);
+    h = std::max(h_floor, std::cbrt(vol / (double)n));
+    const double h_hint_floor = max_dist_hint > 0.0 ? max_dist_hint / 64.0 : 0.0;  // bounds ring count
+    h = std::max(h, h_hint_floor);
+    for (int trial = 0; trial < 5; ++trial) {
+      CU_TRY(bin_points(h, nullptr, nullptr));
+      const double ppc = (double)n / (double)std::max<unsigned long long>(occ, 1);
+      if (ppc > 0.75 * target_ppc && ppc < 1.35 * target_ppc) break;
+      double f = std::sqrt(target_ppc / ppc);
+      f = std::min(std::max(f, 0.25), 4.0);
+      const double hn = std::max(std::max(h * f, h_floor), h_hint_floor);
+      if (std::fabs(hn - h) < 1e-3 * h) break;
+      h = hn;
+    }
+  }
+  if (!(h > 0.0) || !std::isfinite(h)) return fail(B200ICP_EINVAL, "scan_create: bad cell edge");
+
+  // ---- final binning + sort
+  DevBuf<uint32_t> keys_in, keys_out, vals_in;
+  b200icp_scan* sc = new b200icp_scan();
+  auto bail = [&](int code, const std::string& msg) { delete sc; return fail(code, msg); };
+  if (keys_in.alloc(n) != cudaSuccess || keys_out.alloc(n) != cudaSuccess ||
+      vals_in.alloc(n) != cudaSuccess || sc->perm.alloc(n) != cudaSuccess)
+    return bail(B200ICP_ENOMEM, "scan_create: device allocation failed (sort buffers)");
+  cudaError_t e = bin_points(h, keys_in.p, vals_in.p);
+  if (e != cudaSuccess) return bail(B200ICP_ECUDA, std::string("scan_create: binning: ") + cudaGetErrorString(e));
+  const size_t ncells = (size_t)dims[0] * dims[1] * dims[2];
+  int key_bits = 1;
+  while ((1ull << key_bits) < ncells && key_bits < 32) ++key_bits;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, sc->perm.p,
+                                  (int)n, 0, key_bits, st);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts.p, counts.p, (int)(ncells + 1), st);
+  DevBuf<unsigned char> tmp;
+  if (tmp.alloc(std::max(tmp_bytes, scan_bytes) + 256) != cudaSuccess ||
+      sc->cell_start.alloc(ncells + 1) != cudaSuccess || sc->p32.alloc(n) != cudaSuccess ||
+      sc->p64.alloc(n) != cudaSuccess || (d_normals && sc->nrm.alloc(n) != cudaSuccess))
+    return bail(B200ICP_ENOMEM, "scan_create: device allocation failed (grid buffers)");
+  cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, sc->perm.p, (int)n,
+                                  0, key_bits, st);
+  cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, counts.p, sc->cell_start.p, (int)(ncells + 1), st);
+  const unsigned gblocks = (unsigned)((n + 255) / 256);
+  DevBuf<float> bmax_part;
+  if (bmax_part.alloc(gblocks) != cudaSuccess) return bail(B200ICP_ENOMEM, "scan_create: alloc");
+  const double c[3] = {0.5 * (bb[0] + bb[3]), 0.5 * (bb[1] + bb[4]), 0.5 * (bb[2] + bb[5])};
+  gather_kernel<<<gblocks, 256, 0, st>>>(d_xyz, d_normals, n, sc->perm.p, c[0], c[1], c[2], sc->p32.p,
+                                         sc->p64.p, sc->nrm.p, bmax_part.p);
+  std::vector<float> bm(gblocks);
+  e = cudaMemcpyAsync(bm.data(), bmax_part.p, gblocks * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return bail(B200ICP_ECUDA, std::string("scan_create: ") + cudaGetErrorString(e));
+  float bmax = 0.f;
+  for (float v : bm) bmax = std::max(bmax, v);
+
+  sc->n = n;
+  sc->has_normals = d_normals != nullptr;
+  sc->n_cells = ncells;
+  sc->n_occupied = occ;
+  GridDev& g = sc->g;
+  for (int k = 0; k < 3; ++k) { g.g0[k] = bb[k]; g.c[k] = c[k]; g.bbox_lo[k] = bb[k]; g.bbox_hi[k] = bb[3 + k]; }
+  g.h = h; g.inv_h = 1.0 / h;
+  g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+  g.n = (uint32_t)n;
+  g.bmax = bmax * 1.0000002f + 1e-30f;
+  g.cell_start = sc->cell_start.p;
+  g.p32 = sc->p32.p;
+  g.p64 = sc->p64.p;
+  g.nrm = sc->nrm.p;
+  m4_identity(sc->transMat);
+  m4_identity(sc->dalignxf);
+  for (int i = 0; i < 9; ++i) sc->nmat[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  *out = sc;
+  return B200ICP_OK;
+}
+
+int b200icp_scan_create(b200icp_ctx* ctx, const double* xyz, const double* normals, size_t n,
+                        double cell_edge, double max_dist_hint, b200icp_scan** out) {
+  if (!ctx || !out) return fail(B200ICP_EINVAL, "scan_create: NULL argument");
+  *out = nullptr;
+  if (n == 0) return fail(B200ICP_EEMPTY, "scan_create: cannot build a search grid over zero points");
+  if (!xyz) return fail(B200ICP_EINVAL, "scan_create: xyz is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  DevBuf<double> d_xyz, d_nrm;
+  CU_TRY(d_xyz.alloc(3 * n));
+  CU_TRY(cudaMemcpyAsync(d_xyz.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (normals) {
+    CU_TRY(d_nrm.alloc(3 * n));
+    CU_TRY(cudaMemcpyAsync(d_nrm.p, normals, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = b200icp_scan_create_device(ctx, d_xyz.p, normals ? d_nrm.p : nullptr, n, cell_edge,
+                                      max_dist_hint, out);
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+void b200icp_scan_destroy(b200icp_ctx* ctx, b200icp_scan* scan) {
+  if (!scan) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  delete scan;
+}
+
+size_t b200icp_scan_size(const b200icp_scan* scan) { return scan ? scan->n : 0; }
+
+int b200icp_scan_grid_info(const b200icp_scan* scan, int dims[3], double* cell_edge, uint64_t* n_cells,
+                           uint64_t* n_occupied) {
+  if (!scan) return fail(B200ICP_EINVAL, "scan is NULL");
+  if (dims) { dims[0] = scan->g.nx; dims[1] = scan->g.ny; dims[2] = scan->g.nz; }
+  if (cell_edge) *cell_edge = scan->g.h;
+  if (n_cells) *n_cells = scan->n_cells;
+  if (n_occupied) *n_occupied = scan->n_occupied;
+  return B200ICP_OK;
+}
+
+int b200icp_scan_get_pose(const b200icp_scan* scan, double transMat[16], double dalignxf[16]) {
+  if (!scan) return fail(B200ICP_EINVAL, "scan is NULL");
+  if (transMat) memcpy(transMat, scan->transMat, sizeof scan->transMat);
+  if (dalignxf) memcpy(dalignxf, scan->dalignxf, sizeof scan->dalignxf);
+  return B200ICP_OK;
+}
+
+int b200icp_scan_set_pose(b200icp_scan* scan, const double transMat[16], const double dalignxf[16]) {
+  if (!scan) return fail(B200ICP_EINVAL, "scan is NULL");
+  if (transMat) memcpy(scan->transMat, transMat, sizeof scan->transMat);
+  if (dalignxf) {
+    memcpy(scan->dalignxf, dalignxf, sizeof scan->dalignxf);
+    // normals follow the rotation history (transform3normal); a freshly set pose restarts it with
+    // the transposed rotation block of dalignxf, which is what a single Scan::transform would leave.
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) scan->nmat[3 * r + c] = dalignxf[4 * r + c];
+  }
+  return B200ICP_OK;
+}
+
+int b200icp_scan_download(b200icp_ctx* ctx, const b200icp_scan* scan, double* xyz_out, double* nrm_out) {
+  if (!ctx || !scan || !xyz_out) return fail(B200ICP_EINVAL, "scan_download: NULL argument");
+  if (nrm_out && !scan->has_normals) return fail(B200ICP_ESTATE, "scan_download: scan has no normals");
+  CU_TRY(cudaSetDevice(ctx->device));
+  DevBuf<double> d_xyz, d_nrm, d_xf;
+  CU_TRY(d_xyz.alloc(3 * scan->n));
+  if (nrm_out) CU_TRY(d_nrm.alloc(3 * scan->n));
+  CU_TRY(d_xf.alloc(25));
+  double hx[25];
+  memcpy(hx, scan->dalignxf, 16 * sizeof(double));
+  memcpy(hx + 16, scan->nmat, 9 * sizeof(double));
+  CU_TRY(cudaMemcpyAsync(d_xf.p, hx, sizeof hx, cudaMemcpyHostToDevice, ctx->stream));
+  scan_export_kernel<<<(unsigned)((scan->n + 255) / 256), 256, 0, ctx->stream>>>(
+      scan->g.p64, scan->g.nrm, scan->perm.p, (uint32_t)scan->n, d_xf.p, d_xyz.p, nrm_out ? d_nrm.p : nullptr);
+  CU_TRY(cudaMemcpyAsync(xyz_out, d_xyz.p, 3 * scan->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nrm_out)
+    CU_TRY(cudaMemcpyAsync(nrm_out, d_nrm.p, 3 * scan->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaGetLastError());
+  return B200ICP_OK;
+}
+
+// ----------------------------------------------------------------------------- API search path
+int b200icp_nn_batch_device(b200icp_ctx* ctx, const b200icp_scan* model, const double* d_q_xyz,
+                            const double* d_q_nrm, size_t n, const double source_alignxf[16],
+                            double maxdist2, int pairing_mode, int32_t* d_idx_out, double* d_d2_out,
+                            double sums_out[8]) {
+  if (!ctx || !model) return fail(B200ICP_EINVAL, "nn_batch: NULL argument");
+  if (pairing_mode != B200ICP_CLOSEST_POINT && pairing_mode != B200ICP_CLOSEST_PLANE_SIMPLE)
+    return fail(B200ICP_EINVAL, "nn_batch: pairing mode not on the accelerated path");
+  if (pairing_mode == B200ICP_CLOSEST_PLANE_SIMPLE && !d_q_nrm)
+    return fail(B200ICP_EINVAL, "nn_batch: CLOSEST_PLANE_SIMPLE needs query normals");
+  if (!(maxdist2 >= 0.0)) return fail(B200ICP_EINVAL, "nn_batch: maxdist2 must be >= 0");
+  if (sums_out) for (int k = 0; k < 8; ++k) sums_out[k] = 0.0;
+  if (n == 0) return B200ICP_OK;
+  if (!d_q_xyz) return fail(B200ICP_EINVAL, "nn_batch: q_xyz is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  double id[16];
+  m4_identity(id);
+  const double* S = source_alignxf ? source_alignxf : id;
+  memcpy(ctx->h_small, S, 16 * sizeof(double));
+  m4_inverse(S, ctx->h_small + 16);
+  CU_TRY(cudaMemcpyAsync(ctx->d_small.p, ctx->h_small, 32 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->blocks_per_sm_batch == 0) {
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, nn_batch_kernel<false>, kBlock, 0);
+    ctx->blocks_per_sm_batch = std::max(b, 1);
+  }
+  const size_t ntiles = (n + kBlock - 1) / kBlock;
+  const int grid = (int)std::min<size_t>(ntiles, (size_t)std::min(ctx->sm_count * ctx->blocks_per_sm_batch,
+                                                                  max_iter_grid(ctx)));
+  if (pairing_mode == B200ICP_CLOSEST_PLANE_SIMPLE)
+    nn_batch_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(model->g, d_q_xyz, d_q_nrm, n, ctx->d_small.p,
+                                                            maxdist2, d_idx_out, d_d2_out, ctx->partials.p);
+  else
+    nn_batch_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(model->g, d_q_xyz, d_q_nrm, n, ctx->d_small.p,
+                                                             maxdist2, d_idx_out, d_d2_out, ctx->partials.p);
+  CU_TRY(cudaGetLastError());
+  if (sums_out) {
+    std::vector<double> hp((size_t)grid * 8);
+    CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 8; ++k) sums_out[k] += hp[(size_t)b * 8 + k];
+  }
+  return B200ICP_OK;
+}
+
+int b200icp_nn_batch(b200icp_ctx* ctx, const b200icp_scan* model, const double* q_xyz,
+                     const double* q_nrm, size_t n, const double source_alignxf[16], double maxdist2,
+                     int pairing_mode, int32_t* idx_out, double* d2_out, double sums_out[8]) {
+  if (!ctx || !model) return fail(B200ICP_EINVAL, "nn_batch: NULL argument");
+  if (n == 0) {
+    if (sums_out) for (int k = 0; k < 8; ++k) sums_out[k] = 0.0;
+    return B200ICP_OK;
+  }
+  if (!q_xyz) return fail(B200ICP_EINVAL, "nn_batch: q_xyz is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  DevBuf<double> dq, dn, dd2;
+  DevBuf<int32_t> didx;
+  CU_TRY(dq.alloc(3 * n));
+  CU_TRY(didx.alloc(n));
+  if (d2_out) CU_TRY(dd2.alloc(n));
+  CU_TRY(cudaMemcpyAsync(dq.p, q_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (q_nrm) {
+    CU_TRY(dn.alloc(3 * n));
+    CU_TRY(cudaMemcpyAsync(dn.p, q_nrm, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = b200icp_nn_batch_device(ctx, model, dq.p, q_nrm ? dn.p : nullptr, n, source_alignxf, maxdist2,
+                                   pairing_mode, didx.p, d2_out ? dd2.p : nullptr, sums_out);
+  if (rc != B200ICP_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+  if (idx_out)
+    CU_TRY(cudaMemcpyAsync(idx_out, didx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (d2_out)
+    CU_TRY(cudaMemcpyAsync(d2_out, dd2.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaGetLastError());
+  return B200ICP_OK;
+}
+
+int b200icp_find_closest(b200icp_ctx* ctx, const b200icp_scan* model, const double p[3], double maxdist2,
+                         int64_t* idx_out) {
+  if (!p || !idx_out) return fail(B200ICP_EINVAL, "find_closest: NULL argument");
+  int32_t idx = -1;
+  int rc = b200icp_nn_batch(ctx, model, p, nullptr, 1, nullptr, maxdist2, B200ICP_CLOSEST_POINT, &idx,
+                            nullptr, nullptr);
+  if (rc != B200ICP_OK) return rc;
+  *idx_out = idx;
+  return B200ICP_OK;
+}
+
+// -------------------------------------------------------------------------------- fused match
+int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* data,
+                  const b200icp_match_params* prm, double* rms_per_iter, uint64_t* npairs_per_iter,
+                  b200icp_match_result* result) {
+  if (!ctx || !model || !data || !prm) return fail(B200ICP_EINVAL, "match: NULL argument");
+  const int algo = prm->algo;
+  if (algo != 1 && algo != 2 && algo != 6 && algo != 10)
+    return fail(B200ICP_EINVAL, "match: algo must be 1 (QUAT), 2 (SVD), 6 (APX) or 10 (NAPX)");
+  if (prm->pairing_mode != B200ICP_CLOSEST_POINT && prm->pairing_mode != B200ICP_CLOSEST_PLANE_SIMPLE)
+    return fail(B200ICP_EINVAL, "match: pairing mode not on the accelerated path");
+  // reference ctor checks, icp6D.cc:67-78 (there: exit(1))
+  if (prm->max_dist_match < 0.0) return fail(B200ICP_EINVAL, "match: max_dist_match has to be >= 0");
+  if (prm->max_num_iterations < 0) return fail(B200ICP_EINVAL, "match: max_num_iterations has to be >= 0");
+  const bool plane = prm->pairing_mode == B200ICP_CLOSEST_PLANE_SIMPLE;
+  const bool napx = algo == 10;
+  if (plane && !data->has_normals) return fail(B200ICP_ESTATE, "match: CLOSEST_PLANE_SIMPLE needs data normals");
+  if (napx && !plane) return fail(B200ICP_EINVAL, "match: NAPX consumes pair normals; use CLOSEST_PLANE_SIMPLE");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int max_iter = prm->max_num_iterations;
+  b200icp_match_result res;
+  memset(&res, 0, sizeof res);
+  res.queries = data->n;
+  if (max_iter == 0) {  // icp6D.cc:112-114
+    if (result) *result = res;
+    return B200ICP_OK;
+  }
+  CU_TRY(ctx->rms_log.ensure((size_t)max_iter));
+  CU_TRY(ctx->npairs_log.ensure((size_t)max_iter));
+
+  IterState* hs = ctx->h_state;
+  memset(hs, 0, sizeof(IterState));
+  memcpy(hs->X, data->dalignxf, sizeof hs->X);
+  memcpy(hs->T, data->transMat, sizeof hs->T);
+  memcpy(hs->S, model->dalignxf, sizeof hs->S);
+  m4_inverse(hs->S, hs->Sinv);
+  memcpy(hs->Nm, data->nmat, sizeof hs->Nm);
+  xf_point(hs->S, model->g.c, hs->o);
+  m4_identity(hs->alignxf);
+  hs->eps = prm->epsilon_icp;
+  hs->algo = algo;
+  hs->napx_weighted = prm->napx_weighted;
+  hs->max_iter = max_iter;
+  CU_TRY(cudaMemcpyAsync(ctx->d_state.p, hs, sizeof(IterState), cudaMemcpyHostToDevice, st));
+
+  const double maxdist2 = prm->max_dist_match * prm->max_dist_match;
+  const bool exact = prm->exact != 0;
+  const bool profile = prm->profile != 0;
+  if (profile) {
+    const size_t need = std::min<size_t>((size_t)max_iter * 3 + 3, kMaxProfileEvents);
+    while (ctx->events.size() < need) {
+      cudaEvent_t ev;
+      CU_TRY(cudaEventCreate(&ev));
+      ctx->events.push_back(ev);
+    }
+  }
+  const int chunk = 4;
+  int launched = 0, grid = 0;
+  uint32_t launches = 0;
+  int slot = 0;
+  bool done = false;
+  IterState* h_slots = ctx->h_state;  // slot 0 doubles as the upload buffer; copy is ordered after it
+  int pending = -1;
+  size_t ev_i = 0;
+  while (!done && launched < max_iter) {
+    const int todo = std::min(chunk, max_iter - launched);
+    for (int k = 0; k < todo; ++k) {
+      const bool rec = profile && ev_i + 3 <= ctx->events.size();
+      if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i], st));
+      if (launch_iter_dispatch(ctx, napx, plane, exact, model, data, maxdist2, prm->rnd, &grid) != 0)
+        return fail(B200ICP_EINVAL, "match: unsupported kernel variant");
+      if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i + 1], st));
+      icp_solve_kernel<<<1, 384, 0, st>>>(ctx->d_state.p, ctx->partials.p, grid, ctx->rms_log.p,
+                                          ctx->npairs_log.p, ctx->stage2_counter.p);
+      if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
+      launches += 2;
+    }
+    launched += todo;
+    CU_TRY(cudaGetLastError());
+    // poll the previous chunk's state while this chunk runs (speculative launch hides the round trip)
+    if (pending >= 0) {
+      CU_TRY(cudaEventSynchronize(ctx->poll_ev[pending]));
+      if (h_slots[pending].done) done = true;
+    }
+    CU_TRY(cudaMemcpyAsync(&h_slots[slot], ctx->d_state.p, sizeof(IterState), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(ctx->poll_ev[slot], st));
+    pending = slot;
+    slot ^= 1;
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  const IterState& fin = h_slots[pending];
+  res.iterations = fin.done ? fin.ret_iter : max_iter;
+  res.iterations_run = fin.iters_run;
+  res.kernel_launches = launches;
+  res.stage2_queries_last = fin.stage2_last;
+  if (fin.iters_run > 0) {
+    std::vector<double> rms(fin.iters_run);
+    std::vector<unsigned long long> np(fin.iters_run);
+    CU_TRY(cudaMemcpy(rms.data(), ctx->rms_log.p, rms.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(np.data(), ctx->npairs_log.p, np.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    res.rms_last = rms.back();
+    res.npairs_last = np.back();
+    for (int i = 0; i < fin.iters_run; ++i) {
+      if (rms_per_iter) rms_per_iter[i] = rms[i];
+      if (npairs_per_iter) npairs_per_iter[i] = np[i];
+    }
+  }
+  if (profile && ev_i >= 3) {
+    double nn_ms = 0, sv_ms = 0;
+    int cnt = 0;
+    const int lim = std::min<int>(fin.iters_run, (int)(ev_i / 3));
+    for (int i = 0; i < lim; ++i) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, ctx->events[3 * i], ctx->events[3 * i + 1]);
+      cudaEventElapsedTime(&b, ctx->events[3 * i + 1], ctx->events[3 * i + 2]);
+      nn_ms += a; sv_ms += b; ++cnt;
+    }
+    if (cnt) { res.nn_kernel_ms = nn_ms / cnt; res.solve_kernel_ms = sv_ms / cnt; }
+  }
+  memcpy(data->dalignxf, fin.X, sizeof fin.X);
+  memcpy(data->transMat, fin.T, sizeof fin.T);
+  memcpy(data->nmat, fin.Nm, sizeof fin.Nm);
+  if (result) *result = res;
+  return B200ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------ normals
+int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, const double rPos[3],
+                        double* normals_out) {
+  if (!ctx || !xyz || !rPos || !normals_out) return fail(B200ICP_EINVAL, "normals_knn: NULL argument");
+  if (k < 1 || k > 32) return fail(B200ICP_EINVAL, "normals_knn: k must be in [1, 32]");
+  if (n == 0) return fail(B200ICP_EEMPTY, "normals_knn: zero points");
+  b200icp_scan* sc = nullptr;
+  int rc = b200icp_scan_create(ctx, xyz, nullptr, n, 0.0, 0.0, &sc);
+  if (rc != B200ICP_OK) return rc;
+  DevBuf<double> d_out;
+  cudaError_t e = d_out.alloc(3 * n);
+  if (e == cudaSuccess) {
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (k <= 16)
+      normals_knn_kernel<16><<<blocks, 128, 0, ctx->stream>>>(sc->g, sc->perm.p, k, rPos[0], rPos[1], rPos[2], d_out.p);
+    else
+      normals_knn_kernel<32><<<blocks, 128, 0, ctx->stream>>>(sc->g, sc->perm.p, k, rPos[0], rPos[1], rPos[2], d_out.p);
+    e = cudaMemcpyAsync(normals_out, d_out.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  b200icp_scan_destroy(ctx, sc);
+  if (e != cudaSuccess) return fail(B200ICP_ECUDA, std::string("normals_knn: ") + cudaGetErrorString(e));
+  return B200ICP_OK;
+}
+
+}  // extern "C"

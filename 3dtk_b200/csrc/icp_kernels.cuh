@@ -1,0 +1,273 @@
+// icp_kernels.cuh -- the per-iteration kernels of the fused match and the API-compatible batch search.
+//
+//   icp_iter_kernel   one launch per ICP iteration: for every data point  t = X d0,  s = Sinv t,
+//                     exact NN of s in the model grid, rejection d^2 < maxdist2, pair formation
+//                     (incl. CLOSEST_PLANE_SIMPLE projection) and accumulation of the pair moments.
+//                     Replaces Scan::getPtPairs + SearchTree::getPtPairs + the pair walk of Align
+//                     (reference src/slam6d/scan.cc:1220-1260, searchTree.cc:92-188,
+//                     icp6Dquat.cc:57-71) and makes Scan::transformReduced (scan.cc:851-875)
+//                     disappear: the cumulative transform is applied on load.
+//   icp_solve_kernel  one tiny launch per iteration: fixed-order reduction of the per-block moments,
+//                     the 6-DoF solve (solve.h), pose composition (scan.cc:878-898) and the
+//                     convergence test of icp6D::match (icp6D.cc:266-279), all in fp64 on device.
+//   nn_batch_kernel   SearchTree::getPtPairs for caller-supplied queries (API path).
+#pragma once
+#include "nn_search.cuh"
+
+namespace b200 {
+
+struct XfSmem {
+  double X[16], Sinv[16], S[16], Nm[9], o[3];
+};
+
+__device__ __forceinline__ void xf_apply(const double* M, double x, double y, double z, double& ox,
+                                         double& oy, double& oz) {
+  ox = x * M[0] + y * M[4] + z * M[8] + M[12];
+  oy = x * M[1] + y * M[5] + z * M[9] + M[13];
+  oz = x * M[2] + y * M[6] + z * M[10] + M[14];
+}
+
+// transform3 with the reference's rounding (left-to-right, no contraction), for the API path where
+// the query array arrives bit-identical to the reference's.
+__device__ __forceinline__ void xf_apply_strict(const double* M, double x, double y, double z,
+                                                double& ox, double& oy, double& oz) {
+  ox = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, M[0]), __dmul_rn(y, M[4])), __dmul_rn(z, M[8])), M[12]);
+  oy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, M[1]), __dmul_rn(y, M[5])), __dmul_rn(z, M[9])), M[13]);
+  oz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, M[2]), __dmul_rn(y, M[6])), __dmul_rn(z, M[10])), M[14]);
+}
+
+__device__ __forceinline__ unsigned hash32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+template <int NS>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double* __restrict__ out) {
+  __shared__ double red[kWarps][NS_MAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double v = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) v += red[w][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+template <bool NAPX, bool PLANE, bool EXACT>
+__global__ void __launch_bounds__(kBlock, 2)
+icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __restrict__ dn,
+                uint32_t nd, const IterState* __restrict__ st, double maxdist2, int rnd,
+                double* __restrict__ partials, unsigned* __restrict__ stage2_counter) {
+  if (st->done) return;
+  constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
+  __shared__ SearchSmem sm;
+  __shared__ XfSmem xf;
+  const int tid = threadIdx.x;
+  if (tid < 16) { xf.X[tid] = st->X[tid]; xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid]; }
+  if (tid < 9) xf.Nm[tid] = st->Nm[tid];
+  if (tid < 3) xf.o[tid] = st->o[tid];
+  const unsigned iter_salt = (unsigned)st->iter * 0x9E3779B9u;
+  __syncthreads();
+
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  unsigned stage2 = 0;
+
+  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  int parity = 0;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+    const uint32_t i = tile * kBlock + tid;
+    bool active = i < nd;
+    if (rnd > 1 && active) active = (hash32(i ^ iter_salt) % (unsigned)rnd) == 0u;
+    double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
+    if (active) {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
+      const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
+      xf_apply(xf.X, a.x, a.y, z0, tx, ty, tz);
+      xf_apply(xf.Sinv, tx, ty, tz, sx, sy, sz);
+    }
+    int bj;
+    double bd2;
+    unsigned boidx;
+    nn_block_search<EXACT>(model, active, sx, sy, sz, maxdist2, sm, parity, bj, bd2, boidx, stage2);
+    if (active && bj >= 0) {
+      const double2 pa = __ldg(reinterpret_cast<const double2*>(model.p64 + bj));
+      const double pz = __ldg(reinterpret_cast<const double*>(model.p64 + bj) + 2);
+      double p1[3], p2[3] = {tx, ty, tz};
+      xf_apply(xf.S, pa.x, pa.y, pz, p1[0], p1[1], p1[2]);
+      double nv[3] = {0, 0, 0};
+      if (PLANE) {
+        const double2 na = __ldg(reinterpret_cast<const double2*>(dn + i));
+        const double n2 = __ldg(reinterpret_cast<const double*>(dn + i) + 2);
+        nv[0] = xf.Nm[0] * na.x + xf.Nm[1] * na.y + xf.Nm[2] * n2;
+        nv[1] = xf.Nm[3] * na.x + xf.Nm[4] * na.y + xf.Nm[5] * n2;
+        nv[2] = xf.Nm[6] * na.x + xf.Nm[7] * na.y + xf.Nm[8] * n2;
+        const double nl = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);  // Normalize3
+        nv[0] /= nl; nv[1] /= nl; nv[2] /= nl;
+        // s <- (n.(s-t)) n + t   (searchTree.cc:149-162)
+        const double dot = nv[0] * (p1[0] - p2[0]) + nv[1] * (p1[1] - p2[1]) + nv[2] * (p1[2] - p2[2]);
+        p1[0] = nv[0] * dot + p2[0];
+        p1[1] = nv[1] * dot + p2[1];
+        p1[2] = nv[2] * dot + p2[2];
+      }
+      if (NAPX) accumulate_napx(acc, p1, p2, nv, xf.o);
+      else accumulate_p2p(acc, p1, p2, xf.o);
+    }
+  }
+  block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+  if (tid == 0 && stage2) atomicAdd(stage2_counter, stage2);
+}
+
+// One block of 384 threads.  Deterministic: 8 interleaved slices per moment, combined in a fixed tree.
+__global__ void __launch_bounds__(384)
+icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials, int nblocks,
+                 double* __restrict__ rms_log, unsigned long long* __restrict__ npairs_log,
+                 unsigned* __restrict__ stage2_counter) {
+  if (st->done) return;
+  __shared__ double part[NS_MAX][8];
+  __shared__ double mom[NS_MAX];
+  const int tid = threadIdx.x;
+  const int NS = moment_count(st->algo);
+  const int k = tid >> 3, sl = tid & 7;
+  if (k < NS) {
+    double v = 0.0;
+    for (int b = sl; b < nblocks; b += 8) v += partials[(size_t)b * NS_MAX + k];
+    part[k][sl] = v;
+  }
+  __syncthreads();
+  if (tid < NS)
+    mom[tid] = ((part[tid][0] + part[tid][1]) + (part[tid][2] + part[tid][3])) +
+               ((part[tid][4] + part[tid][5]) + (part[tid][6] + part[tid][7]));
+  __syncthreads();
+  if (tid != 0) return;
+
+  // ---- icp6D::match loop body after getPtPairs (icp6D.cc:124-125, :229-279)
+  const int iter = st->iter;
+  st->prev_prev_ret = st->prev_ret;
+  st->prev_ret = st->ret;
+  st->stage2_last = *stage2_counter;
+  *stage2_counter = 0;
+  const double np = mom[0];
+  if (!(np > 3.0)) {  // "do we have enough point pairs?" -> break before any transform
+    st->done = 1;
+    st->ret_iter = iter;
+    return;
+  }
+  double alignxf[16];
+  for (int i = 0; i < 16; ++i) alignxf[i] = st->alignxf[i];  // kept when the Cholesky path bails out
+  const double ret = solve_any(st->algo, mom, st->o, st->napx_weighted, alignxf);
+  st->ret = ret;
+  for (int i = 0; i < 16; ++i) st->alignxf[i] = alignxf[i];
+  rms_log[st->iters_run] = ret;
+  npairs_log[st->iters_run] = (unsigned long long)(np + 0.5);
+  st->iters_run += 1;
+  // Scan::transformMatrix (scan.cc:878-898): transMat <- alignxf*transMat, dalignxf <- alignxf*dalignxf
+  double tmp[16];
+  m4_mul(alignxf, st->X, tmp);
+  for (int i = 0; i < 16; ++i) st->X[i] = tmp[i];
+  m4_mul(alignxf, st->T, tmp);
+  for (int i = 0; i < 16; ++i) st->T[i] = tmp[i];
+  // transform3normal (globals.icc:1465-1475) multiplies by the transposed rotation block:
+  // Nm <- R^T Nm, R(r,c) = alignxf[4c+r]
+  double nn[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      nn[3 * r + c] = alignxf[4 * r + 0] * st->Nm[c] + alignxf[4 * r + 1] * st->Nm[3 + c] +
+                      alignxf[4 * r + 2] * st->Nm[6 + c];
+  for (int i = 0; i < 9; ++i) st->Nm[i] = nn[i];
+  if ((fabs(ret - st->prev_ret) < st->eps && fabs(ret - st->prev_prev_ret) < st->eps) ||
+      iter == st->max_iter - 1) {
+    st->done = 1;
+    st->ret_iter = iter;
+  } else {
+    st->iter = iter + 1;
+  }
+}
+
+// ---- API path: SearchTree::getPtPairs over caller-supplied queries ---------------------------------
+// xf: [0..15] source_alignxf, [16..31] its inverse.  partials: [grid][8] = n, sum, cm[3], cd[3].
+template <bool PLANE>
+__global__ void __launch_bounds__(kBlock)
+nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* __restrict__ q_nrm,
+                size_t n, const double* __restrict__ xfs, double maxdist2, int32_t* __restrict__ idx_out,
+                double* __restrict__ d2_out, double* __restrict__ partials) {
+  __shared__ SearchSmem sm;
+  __shared__ double S[16], Sinv[16];
+  const int tid = threadIdx.x;
+  if (tid < 16) { S[tid] = xfs[tid]; Sinv[tid] = xfs[16 + tid]; }
+  __syncthreads();
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  unsigned stage2 = 0;
+  const size_t ntiles = (n + kBlock - 1) / kBlock;
+  int parity = 0;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+    const size_t i = tile * kBlock + tid;
+    const bool active = i < n;
+    double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
+    if (active) {
+      tx = q_xyz[3 * i]; ty = q_xyz[3 * i + 1]; tz = q_xyz[3 * i + 2];
+      xf_apply_strict(Sinv, tx, ty, tz, sx, sy, sz);
+    }
+    int bj;
+    double bd2;
+    unsigned boidx;
+    nn_block_search<true>(model, active, sx, sy, sz, maxdist2, sm, parity, bj, bd2, boidx, stage2);
+    if (active) {
+      if (idx_out) idx_out[i] = bj >= 0 ? (int32_t)boidx : -1;
+      if (d2_out) d2_out[i] = bj >= 0 ? bd2 : -1.0;
+      if (bj >= 0) {
+        const double2 pa = __ldg(reinterpret_cast<const double2*>(model.p64 + bj));
+        const double pz = __ldg(reinterpret_cast<const double*>(model.p64 + bj) + 2);
+        double p1x, p1y, p1z;
+        xf_apply_strict(S, pa.x, pa.y, pz, p1x, p1y, p1z);
+        if (PLANE) {
+          double nx = q_nrm[3 * i], ny = q_nrm[3 * i + 1], nz = q_nrm[3 * i + 2];
+          const double nl = sqrt(nx * nx + ny * ny + nz * nz);
+          nx /= nl; ny /= nl; nz /= nl;
+          const double dot = nx * (p1x - tx) + ny * (p1y - ty) + nz * (p1z - tz);
+          p1x = nx * dot + tx; p1y = ny * dot + ty; p1z = nz * dot + tz;
+        }
+        const double ex = p1x - tx, ey = p1y - ty, ez = p1z - tz;
+        acc[0] += 1.0;
+        acc[1] += ex * ex + ey * ey + ez * ez;
+        acc[2] += p1x; acc[3] += p1y; acc[4] += p1z;
+        acc[5] += tx; acc[6] += ty; acc[7] += tz;
+      }
+    }
+  }
+  block_reduce_store<8>(acc, partials + (size_t)blockIdx.x * 8);
+}
+
+// current "xyz reduced" = X * original (Scan::transformReduced), written back in original row order
+__global__ void scan_export_kernel(const double4* __restrict__ p64, const double4* __restrict__ nrm,
+                                   const uint32_t* __restrict__ perm, uint32_t n,
+                                   const double* __restrict__ xf /* X[16], Nm[9] */,
+                                   double* __restrict__ xyz_out, double* __restrict__ nrm_out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const size_t dst = perm[j];
+  const double4 p = p64[j];
+  double x, y, z;
+  xf_apply(xf, p.x, p.y, p.z, x, y, z);
+  xyz_out[3 * dst] = x; xyz_out[3 * dst + 1] = y; xyz_out[3 * dst + 2] = z;
+  if (nrm_out && nrm) {
+    const double4 q = nrm[j];
+    const double* Nm = xf + 16;
+    nrm_out[3 * dst] = Nm[0] * q.x + Nm[1] * q.y + Nm[2] * q.z;
+    nrm_out[3 * dst + 1] = Nm[3] * q.x + Nm[4] * q.y + Nm[5] * q.z;
+    nrm_out[3 * dst + 2] = Nm[6] * q.x + Nm[7] * q.y + Nm[8] * q.z;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- ICP correspondences/sec (and iterations/sec) on a 1M-point synthetic scan pair.
+
+Workload (BASELINE.json configs[1]): synthetic 2-scan pair, 1M points each, known SE(3) offset,
+point-to-point icp6D_QUAT, max_dist 25 cm, <= 50 iterations, epsICP 1e-5, no subsampling.
+One "step" = one full icp6D::match of the pair (all iterations until the reference's convergence test
+fires).  Metric = data points searched per second = N_d * iterations / time.
+
+  value      scans + grids already resident in HBM when the timed region starts (CUDA events on the
+             stream the kernels run on, one event pair per step, L2 flushed between steps)
+  e2e        same metric through the public C ABI with HOST (pinned) buffers: upload + grid build of both
+             scans, match, pose read-back, all inside the timed region
+  roofline   correspondence kernel: algorithmic bytes / mean launch time (CUDA events inside the library)
+  cpu_baseline / --impl reference
+             the reference's own CPU path (oracle/_ref: unmodified 3DTK kd.cc / searchTree.cc /
+             icp6Dquat.cc, OpenMP pICP arm, all host cores) on the same pair, bounded iterations
+
+Multi-GPU (--gpus N under torchrun): the path shards by scan pair -- every rank matches its own pair,
+no data-path collective ("scaling": "weak"); time = max over ranks.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "icp_correspondences_per_sec"
+UNIT = "correspondences/s"
+POSE_POS = (12.0, -7.0, 5.0)
+POSE_THETA_DEG = (0.5, -1.0, 0.8)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--exact", type=int, default=1)
+    ap.add_argument("--max-iter", type=int, default=50)
+    ap.add_argument("--cpu-iters", type=int, default=4, help="iterations of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cell-edge", type=float, default=0.0)
+    return ap.parse_args()
+
+
+def make_pair(icp, n, rank):
+    model = icp.synth_scene(7, 42 + 2 * rank, n, 0.5)
+    data = icp.synth_scene(7, 43 + 2 * rank, n, 0.5)
+    Pm = icp.euler_to_matrix4(np.array(POSE_POS), np.deg2rad(np.array(POSE_THETA_DEG)))
+    Pinv, _ = icp.m4inv(Pm)
+    return model, icp.transform_points(Pinv, data), Pm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(model, data, max_iter, steps, warmup):
+    """The reference's OpenMP pICP arm (icp6D.cc:129-222) from oracle/_ref on all host cores."""
+    import orclib
+    from orclib import P
+    L = orclib.ref(omp=True)
+    kind = "reference"
+    if L is None:
+        return None
+    threads = L.ref_max_threads()
+    m = np.ascontiguousarray(model)
+    t0 = time.perf_counter()
+    tree = L.ref_tree_create(P(m), len(m), 0, 20)
+    build_s = time.perf_counter() - t0
+    times, iters = [], []
+    for s in range(warmup + steps):
+        d = np.ascontiguousarray(data).copy()
+        T, D, S = orclib.identity(), orclib.identity(), orclib.identity()
+        rms = np.zeros(max_iter); npairs = np.zeros(max_iter, dtype=np.int64)
+        done, ms = C.c_int(0), C.c_double(0)
+        t0 = time.perf_counter()
+        L.ref_match(tree, P(S), P(d), None, len(d), P(T), P(D), 1, 0, 25.0, max_iter, 1e-5, 1, threads,
+                    P(rms), P(npairs), C.byref(done), C.byref(ms))
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt); iters.append(done.value)
+    L.ref_tree_free(tree)
+    total_t, total_it = sum(times), sum(iters)
+    return {"value": len(data) * total_it / total_t, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "full %d x %d pair, icp6D_QUAT OpenMP arm, first %d iterations per match, %d matches; "
+                      "k-d tree build (%.2f s) excluded as the reference does (icp6D.cc:127)"
+                      % (len(model), len(data), max_iter, steps, build_s),
+            "iters_per_sec": total_it / total_t, "ms_per_step": 1e3 * total_t / max(len(times), 1),
+            "iterations": total_it}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    build = importlib.import_module("3dtk_b200.build")
+    if rank == 0:
+        build.build()
+    icp = importlib.import_module("3dtk_b200")
+
+    config = {"workload": "synthetic 2-scan pair (BASELINE configs[1]): %d pts each, known SE(3) offset, "
+                          "point-to-point icp6D_QUAT, d=25 i=%d epsICP=1e-5" % (a.points, a.max_iter),
+              "points_model": a.points, "points_data": a.points, "algo": "icp6D_QUAT", "max_dist": 25.0,
+              "max_iter": a.max_iter, "eps_icp": 1e-5, "exact_nn": bool(a.exact),
+              "sharding": "one scan pair per GPU, no data-path collective",
+              "l2": "flushed between steps (256 MiB write)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        model, data, _ = make_pair(icp, a.points, 0)
+        r = cpu_reference_run(model, data, a.cpu_iters, a.steps, a.warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref3dtk_omp.so not built"}))
+            return 0
+        config["max_iter"] = a.cpu_iters
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "iters_per_sec": r["iters_per_sec"],
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    ctx = icp.Context(local_rank, stream=stream.cuda_stream)
+
+    model, data, Ptrue = make_pair(icp, a.points, rank)
+    n = a.points
+    # pinned host staging (e2e path)
+    h_model = torch.from_numpy(model).pin_memory()
+    h_data = torch.from_numpy(data).pin_memory()
+    m_scan = icp.Scan.from_host_pointers(ctx, h_model.data_ptr(), None, n, a.cell_edge, 25.0)
+    d_scan = icp.Scan.from_host_pointers(ctx, h_data.data_ptr(), None, n, a.cell_edge, 25.0)
+    ginfo = m_scan.grid_info()
+    eng = icp.icp6D(ctx, algo=icp.ALGO_QUAT, max_dist_match=25.0, max_num_iterations=a.max_iter,
+                    epsilon_icp=1e-5, exact=bool(a.exact))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ident = np.eye(4).reshape(16).copy()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        d_scan.set_pose(ident, ident)
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r = eng.match(m_scan, d_scan)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), r
+
+    for _ in range(a.warmup):
+        resident_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms_total, iters_total, launches = 0.0, 0, 0
+    wall0 = time.perf_counter()
+    last = None
+    for _ in range(a.steps):
+        ms, r = resident_step()
+        ms_total += ms
+        iters_total += r["iterations_run"]
+        launches += int(r["result"].kernel_launches)
+        last = r
+    barrier()
+    clocks = sampler.stop()
+    wall = time.perf_counter() - wall0
+    T_final, _ = d_scan.get_pose()
+    pose_err = float(np.linalg.norm(T_final - Ptrue) / np.linalg.norm(Ptrue))
+
+    # ---- kernel-level timing for the roofline (same workload, CUDA events inside the library)
+    eng_prof = icp.icp6D(ctx, algo=icp.ALGO_QUAT, max_dist_match=25.0, max_num_iterations=a.max_iter,
+                         epsilon_icp=1e-5, exact=bool(a.exact), profile=True)
+    d_scan.set_pose(ident, ident)
+    flush.fill_(1)
+    rp = eng_prof.match(m_scan, d_scan)
+    nn_ms = rp["result"].nn_kernel_ms
+    solve_ms = rp["result"].solve_kernel_ms
+
+    # ---- e2e: host buffers -> upload + grid build -> match -> pose back
+    def e2e_step():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ms_ = icp.Scan.from_host_pointers(ctx, h_model.data_ptr(), None, n, a.cell_edge, 25.0)
+        ds_ = icp.Scan.from_host_pointers(ctx, h_data.data_ptr(), None, n, a.cell_edge, 25.0)
+        r_ = eng.match(ms_, ds_)
+        pose = ds_.get_pose()[0]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ms_.destroy(); ds_.destroy()
+        return dt, r_, pose
+    e2e_steps = max(2, min(a.steps, 5))
+    e2e_step()
+    barrier()
+    e2e_t, e2e_it = 0.0, 0
+    for _ in range(e2e_steps):
+        dt, r_, _ = e2e_step()
+        e2e_t += dt
+        e2e_it += r_["iterations_run"]
+    barrier()
+
+    # ---- reduce over ranks: max time, summed work
+    vals = torch.tensor([ms_total, float(iters_total), e2e_t, float(e2e_it), float(launches)],
+                        dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, e2e_t = float(mx[0]), float(mx[2])
+        iters_sum, e2e_it_sum, launches = float(sm[1]), float(sm[3]), int(sm[4])
+    else:
+        iters_sum, e2e_it_sum = float(iters_total), float(e2e_it)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    value = n * iters_sum / (ms_total * 1e-3)
+    e2e_value = n * e2e_it_sum / e2e_t
+    hbm_peak, peak_src = peaks()
+    n_occ = ginfo["n_occupied"]
+    b_alg = 16.0 * n + 16.0 * n + 8.0 * n_occ + 512.0
+    achieved = b_alg / (nn_ms * 1e-3) / 1e9 if nn_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "icp_iter_kernel<P2P,POINT,%s>" % ("EXACT" if a.exact else "FP32"),
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": b_alg, "kernel_ms": nn_ms, "solve_kernel_ms": solve_ms,
+                "peak_source": peak_src,
+                "note": "B_alg = 16*N_d + 16*N_m + 8*N_occupied_cells + 512 (SURVEY 8d); model fits L2, the "
+                        "kernel is L1/L2-latency and issue bound, see DESIGN.md"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "iters_per_sec": iters_sum / (ms_total * 1e-3), "iterations_per_match": iters_total / a.steps,
+            "pose_rel_frobenius_vs_truth": pose_err, "grid": ginfo, "wall_s_timed_region": wall,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 24,
+                    "d2h_bytes_per_step": 2 * 640 * max(1, (a.max_iter + 3) // 4) + 16 * a.max_iter,
+                    "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches, "roofline": roofline}
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            cb = cpu_reference_run(model, data, a.cpu_iters, 1, 0)
+        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
+            cb = None
+            line["cpu_baseline_error"] = repr(ex)
+        if cb:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["iters_per_sec"] = cb["iters_per_sec"]
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -164,8 +164,12 @@ int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, co
                         double* normals_out);
 
 /* ---- synthetic inputs (host only, no GPU needed) -------------------------
- * scene(seed, n): indoor box scene, area-proportional surface sampling, N(0, noise^2) per coordinate. */
-int b200icp_synth_scene(uint64_t seed, size_t n, double noise_sigma, double* xyz_out);
+ * scene(geom_seed, sample_seed, n): indoor box room 2000x300x1000 cm + 4 interior walls + 20 boxes whose
+ * placement derives from geom_seed; n points sampled area-proportionally on the surfaces from
+ * sample_seed (std::mt19937_64), plus N(0, noise_sigma^2) per coordinate.  Two calls with the same
+ * geom_seed and different sample_seed are independent resamplings of the same geometry. */
+int b200icp_synth_scene(uint64_t geom_seed, uint64_t sample_seed, size_t n, double noise_sigma,
+                        double* xyz_out);
 /* EulerToMatrix4 (globals.icc:501-531) -- exported so every binding builds poses identically. */
 void b200icp_euler_to_matrix4(const double rPos[3], const double rPosTheta[3], double out[16]);
 int b200icp_m4inv(const double in[16], double out[16]);

@@ -282,6 +282,12 @@ void svd_3x3(const double* H, double* U, double* w, double* V) {  // row-major
     }
   }
   memcpy(V, Vs, sizeof Vs);
+  // rank-2 input (e.g. coplanar pairs): like a Householder SVD, return a full orthonormal U
+  if (w[2] == 0.0 && w[1] > 0.0) {
+    U[2] = U[3] * U[7] - U[6] * U[4];
+    U[5] = U[6] * U[1] - U[0] * U[7];
+    U[8] = U[0] * U[4] - U[3] * U[1];
+  }
 }
 
 // ---- Horn's quartic route (icp6Dquat.cc:171-513) ----------------------------------------------

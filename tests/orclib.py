@@ -1,0 +1,163 @@
+"""ctypes loaders for the oracle libraries (test infrastructure).
+
+  port()  -> oracle/_build/liboracle_icp.so   our CPU restatement (built on demand with g++)
+  ref()   -> oracle/_ref/libref3dtk.so        the compiled, unmodified reference (None if absent)
+Both are checkers only; nothing in the product imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE_DIR, "_build", "liboracle_icp.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk.so")
+REF_OMP_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk_omp.so")
+
+vp, cl, ci, cd = C.c_void_p, C.c_long, C.c_int, C.c_double
+_port = None
+_ref = {}
+
+
+def build_port():
+    src = os.path.join(ORACLE_DIR, "oracle_icp.cpp")
+    if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "port"], check=True)
+    return PORT_SO
+
+
+def build_ref():
+    """Compile oracle/_ref from /root/reference when it is present (this container only)."""
+    subprocess.run(["make", "-s", "-j8", "-C", ORACLE_DIR, "ref"], check=True)
+    return os.path.exists(REF_SO)
+
+
+def port():
+    global _port
+    if _port is None:
+        L = C.CDLL(build_port())
+        L.orc_m4inv.restype = ci; L.orc_m4inv.argtypes = [vp, vp]
+        L.orc_mmult.restype = None; L.orc_mmult.argtypes = [vp, vp, vp]
+        L.orc_euler_to_matrix4.restype = None; L.orc_euler_to_matrix4.argtypes = [vp, vp, vp]
+        L.orc_tree_create.restype = vp; L.orc_tree_create.argtypes = [vp, cl, ci]
+        L.orc_tree_free.restype = None; L.orc_tree_free.argtypes = [vp]
+        L.orc_find_closest.restype = cl; L.orc_find_closest.argtypes = [vp, vp, cd]
+        L.orc_find_closest_batch.restype = None
+        L.orc_find_closest_batch.argtypes = [vp, vp, cl, cd, vp, vp]
+        L.orc_brute_closest.restype = cl; L.orc_brute_closest.argtypes = [vp, cl, vp, cd]
+        L.orc_get_pt_pairs.restype = cl
+        L.orc_get_pt_pairs.argtypes = [vp, vp, vp, vp, cl, cl, cd, ci, vp, vp, vp, vp, vp, vp, vp]
+        L.orc_align.restype = cd; L.orc_align.argtypes = [ci, cl, vp, vp, vp, vp, vp, ci, vp]
+        L.orc_match.restype = ci
+        L.orc_match.argtypes = [vp, vp, vp, vp, cl, vp, vp, ci, ci, cd, ci, cd, ci, vp, vp, vp]
+        L.orc_normals_knn.restype = None; L.orc_normals_knn.argtypes = [vp, cl, ci, vp, vp]
+        _port = L
+    return _port
+
+
+def ref(omp=False):
+    path = REF_OMP_SO if omp else REF_SO
+    if path not in _ref:
+        if not os.path.exists(path):
+            _ref[path] = None
+        else:
+            L = C.CDLL(path)
+            L.ref_max_threads.restype = ci
+            L.ref_tree_create.restype = vp; L.ref_tree_create.argtypes = [vp, cl, ci, ci]
+            L.ref_tree_free.restype = None; L.ref_tree_free.argtypes = [vp]
+            L.ref_find_closest.restype = cl; L.ref_find_closest.argtypes = [vp, vp, cd, ci]
+            L.ref_find_closest_batch.restype = None
+            L.ref_find_closest_batch.argtypes = [vp, vp, cl, cd, vp, ci]
+            L.ref_knn.restype = ci; L.ref_knn.argtypes = [vp, vp, ci, vp]
+            L.ref_get_pt_pairs.restype = cl
+            L.ref_get_pt_pairs.argtypes = [vp, vp, vp, vp, cl, cl, ci, ci, cd, ci, vp, vp, vp, vp, vp, vp]
+            L.ref_align.restype = cd; L.ref_align.argtypes = [ci, cl, vp, vp, vp, vp, vp, vp]
+            L.ref_m4inv.restype = ci; L.ref_m4inv.argtypes = [vp, vp]
+            L.ref_mmult.restype = None; L.ref_mmult.argtypes = [vp, vp, vp]
+            L.ref_euler_to_matrix4.restype = None; L.ref_euler_to_matrix4.argtypes = [vp, vp, vp]
+            L.ref_matrix4_to_euler.restype = None; L.ref_matrix4_to_euler.argtypes = [vp, vp, vp]
+            L.ref_match.restype = ci
+            L.ref_match.argtypes = [vp, vp, vp, vp, cl, vp, vp, ci, ci, cd, ci, cd, ci, ci, vp, vp, vp, vp]
+            L.ref_normals_knn.restype = None; L.ref_normals_knn.argtypes = [vp, cl, ci, vp, vp]
+            _ref[path] = L
+    return _ref[path]
+
+
+def P(a):
+    return None if a is None else a.ctypes.data
+
+
+def identity():
+    return np.eye(4).T.reshape(16).copy()
+
+
+# ---- convenience wrappers used by several test files -------------------------------------------
+class PortTree:
+    def __init__(self, xyz, bucket=20):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self.h = port().orc_tree_create(P(self.xyz), len(self.xyz), bucket)
+
+    def find_closest_batch(self, q, maxdist2):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        idx = np.empty(len(q), np.int32)
+        d2 = np.empty(len(q))
+        port().orc_find_closest_batch(self.h, P(q), len(q), maxdist2, P(idx), P(d2))
+        return idx, d2
+
+    def get_pt_pairs(self, src_xf, data_xyz, data_nrm, maxdist2, mode):
+        n = len(data_xyz)
+        p1, p2, pn = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3))
+        idx = np.empty(n, np.int32)
+        s, cm, cdv = np.zeros(1), np.zeros(3), np.zeros(3)
+        k = port().orc_get_pt_pairs(self.h, P(src_xf), P(data_xyz), P(data_nrm), 0, n, maxdist2, mode,
+                                    P(p1), P(p2), P(pn), P(idx), P(s), P(cm), P(cdv))
+        return k, p1[:k], p2[:k], pn[:k], idx[:k], s[0], cm, cdv
+
+    def __del__(self):
+        try:
+            port().orc_tree_free(self.h)
+        except Exception:
+            pass
+
+
+def port_match(model_xyz, data_xyz, data_nrm=None, algo=1, mode=0, max_dist=25.0, max_iter=50, eps=1e-5,
+               model_dalignxf=None, napx_weighted=0):
+    """icp6D::match serial arm on the restatement. Returns dict with transmat, rms, npairs, iterations."""
+    tree = PortTree(model_xyz)
+    d = np.ascontiguousarray(data_xyz, dtype=np.float64).copy()
+    nrm = None if data_nrm is None else np.ascontiguousarray(data_nrm, dtype=np.float64).copy()
+    T, D = identity(), identity()
+    S = identity() if model_dalignxf is None else np.ascontiguousarray(model_dalignxf, dtype=np.float64)
+    rms = np.zeros(max(max_iter, 1)); npairs = np.zeros(max(max_iter, 1), dtype=np.int64)
+    done = C.c_int(0)
+    it = port().orc_match(tree.h, P(S), P(d), P(nrm), len(d), P(T), P(D), algo, mode, max_dist, max_iter,
+                          eps, napx_weighted, P(rms), P(npairs), C.byref(done))
+    k = done.value
+    return {"iterations": it, "iterations_run": k, "transmat": T, "dalignxf": D, "rms": rms[:k],
+            "npairs": npairs[:k], "xyz": d, "nrm": nrm}
+
+
+def ref_match(model_xyz, data_xyz, data_nrm=None, algo=1, mode=0, max_dist=25.0, max_iter=50, eps=1e-5,
+              model_dalignxf=None, threads=0, omp=False):
+    L = ref(omp)
+    m = np.ascontiguousarray(model_xyz, dtype=np.float64)
+    tree = L.ref_tree_create(P(m), len(m), 0, 20)
+    d = np.ascontiguousarray(data_xyz, dtype=np.float64).copy()
+    nrm = None if data_nrm is None else np.ascontiguousarray(data_nrm, dtype=np.float64).copy()
+    T, D = identity(), identity()
+    S = identity() if model_dalignxf is None else np.ascontiguousarray(model_dalignxf, dtype=np.float64)
+    rms = np.zeros(max(max_iter, 1)); npairs = np.zeros(max(max_iter, 1), dtype=np.int64)
+    done = C.c_int(0); ms = C.c_double(0)
+    it = L.ref_match(tree, P(S), P(d), P(nrm), len(d), P(T), P(D), algo, mode, max_dist, max_iter, eps, 1,
+                     threads, P(rms), P(npairs), C.byref(done), C.byref(ms))
+    L.ref_tree_free(tree)
+    k = done.value
+    return {"iterations": it, "iterations_run": k, "transmat": T, "dalignxf": D, "rms": rms[:k],
+            "npairs": npairs[:k], "xyz": d, "nrm": nrm, "ms_after_first": ms.value}
+
+
+def rel_frobenius(a, b):
+    a, b = np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
