@@ -73,6 +73,7 @@ def _load():
         "b200icp_nn_batch_device": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
         "b200icp_align_pairs": (i32, [i32, sz, dp, dp, dp, dp, dp, dp, C.POINTER(f64)]),
         "b200icp_match": (i32, [vp, vp, vp, C.POINTER(MatchParams), dp, dp, C.POINTER(MatchResult)]),
+        "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
         "b200icp_euler_to_matrix4": (None, [dp, dp, dp]),
@@ -290,7 +291,12 @@ class icp6D:
         _check(lib.b200icp_match(self.ctx._h, previous_scan._h, current_scan._h, C.byref(p), _ptr(rms),
                                  _ptr(npairs), C.byref(res)))
         k = res.iterations_run
-        return {"iterations": res.iterations, "iterations_run": k, "rms": rms[:k].copy(),
+        prof = None
+        if k > 0:
+            nn, sv, s2 = np.zeros(k), np.zeros(k), np.zeros(k, dtype=np.uint32)
+            lib.b200icp_last_profile(self.ctx._h, k, _ptr(nn), _ptr(sv), _ptr(s2))
+            prof = {"nn_ms": nn, "solve_ms": sv, "stage2": s2}
+        return {"profile": prof, "iterations": res.iterations, "iterations_run": k, "rms": rms[:k].copy(),
                 "npairs": npairs[:k].copy(), "result": res}
 
 

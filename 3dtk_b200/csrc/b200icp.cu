@@ -78,6 +78,10 @@ struct b200icp_ctx {
   DevBuf<double> rms_log;
   DevBuf<unsigned long long> npairs_log;
   DevBuf<unsigned> stage2_counter;
+  DevBuf<unsigned> stage2_log;
+  DevBuf<int> nn_cache;             // per data point: neighbour of the previous iteration
+  std::vector<double> prof_nn_ms, prof_solve_ms;   // last profiled match, per iteration
+  std::vector<unsigned> prof_stage2;
   DevBuf<double> d_small;           // 64 doubles of scratch (transforms for API kernels)
   double* h_small = nullptr;        // pinned 64 doubles
   std::vector<cudaEvent_t> events;
@@ -129,7 +133,8 @@ void launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const
       ntiles, (uint32_t)(ctx->sm_count * std::min(ctx->blocks_per_sm[variant], kMaxBlocksPerSm)));
   *grid_out = grid;
   kern<<<grid, kBlock, 0, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p,
-                                         maxdist2, rnd, ctx->partials.p, ctx->stage2_counter.p);
+                                         maxdist2, rnd, ctx->nn_cache.p, ctx->partials.p,
+                                         ctx->stage2_counter.p);
 }
 
 int launch_iter_dispatch(b200icp_ctx* ctx, bool napx, bool plane, bool exact,
@@ -213,6 +218,8 @@ void b200icp_destroy(b200icp_ctx* ctx) {
   ctx->rms_log.release();
   ctx->npairs_log.release();
   ctx->stage2_counter.release();
+  ctx->stage2_log.release();
+  ctx->nn_cache.release();
   ctx->d_small.release();
   if (ctx->own) cudaStreamDestroy(ctx->own);
   delete ctx;
@@ -571,6 +578,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   }
   CU_TRY(ctx->rms_log.ensure((size_t)max_iter));
   CU_TRY(ctx->npairs_log.ensure((size_t)max_iter));
+  CU_TRY(ctx->stage2_log.ensure((size_t)max_iter));
+  CU_TRY(ctx->nn_cache.ensure(data->n));
 
   IterState* hs = ctx->h_state;
   memset(hs, 0, sizeof(IterState));
@@ -586,6 +595,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   hs->napx_weighted = prm->napx_weighted;
   hs->max_iter = max_iter;
   CU_TRY(cudaMemcpyAsync(ctx->d_state.p, hs, sizeof(IterState), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemsetAsync(ctx->nn_cache.p, 0xFF, data->n * sizeof(int), st));  // -1: no cached neighbour
 
   const double maxdist2 = prm->max_dist_match * prm->max_dist_match;
   const bool exact = prm->exact != 0;
@@ -615,7 +625,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
         return fail(B200ICP_EINVAL, "match: unsupported kernel variant");
       if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i + 1], st));
       icp_solve_kernel<<<1, 384, 0, st>>>(ctx->d_state.p, ctx->partials.p, grid, ctx->rms_log.p,
-                                          ctx->npairs_log.p, ctx->stage2_counter.p);
+                                          ctx->npairs_log.p, ctx->stage2_log.p, ctx->stage2_counter.p);
       if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
       launches += 2;
     }
@@ -650,6 +660,12 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
       if (npairs_per_iter) npairs_per_iter[i] = np[i];
     }
   }
+  ctx->prof_nn_ms.clear(); ctx->prof_solve_ms.clear(); ctx->prof_stage2.clear();
+  if (fin.iters_run > 0) {
+    ctx->prof_stage2.resize(fin.iters_run);
+    CU_TRY(cudaMemcpy(ctx->prof_stage2.data(), ctx->stage2_log.p, fin.iters_run * sizeof(unsigned),
+                      cudaMemcpyDeviceToHost));
+  }
   if (profile && ev_i >= 3) {
     double nn_ms = 0, sv_ms = 0;
     int cnt = 0;
@@ -658,6 +674,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, ctx->events[3 * i], ctx->events[3 * i + 1]);
       cudaEventElapsedTime(&b, ctx->events[3 * i + 1], ctx->events[3 * i + 2]);
+      ctx->prof_nn_ms.push_back(a); ctx->prof_solve_ms.push_back(b);
       nn_ms += a; sv_ms += b; ++cnt;
     }
     if (cnt) { res.nn_kernel_ms = nn_ms / cnt; res.solve_kernel_ms = sv_ms / cnt; }
@@ -667,6 +684,17 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   memcpy(data->nmat, fin.Nm, sizeof fin.Nm);
   if (result) *result = res;
   return B200ICP_OK;
+}
+
+int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  const int n = (int)ctx->prof_stage2.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (nn_ms) nn_ms[i] = i < (int)ctx->prof_nn_ms.size() ? ctx->prof_nn_ms[i] : 0.0;
+    if (solve_ms) solve_ms[i] = i < (int)ctx->prof_solve_ms.size() ? ctx->prof_solve_ms[i] : 0.0;
+    if (stage2) stage2[i] = ctx->prof_stage2[i];
+  }
+  return n;
 }
 
 // ------------------------------------------------------------------------------------ normals

@@ -65,7 +65,8 @@ template <bool NAPX, bool PLANE, bool EXACT>
 __global__ void __launch_bounds__(kBlock, 2)
 icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __restrict__ dn,
                 uint32_t nd, const IterState* __restrict__ st, double maxdist2, int rnd,
-                double* __restrict__ partials, unsigned* __restrict__ stage2_counter) {
+                int* __restrict__ nn_cache, double* __restrict__ partials,
+                unsigned* __restrict__ stage2_counter) {
   if (st->done) return;
   constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
   __shared__ SearchSmem sm;
@@ -83,22 +84,24 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   unsigned stage2 = 0;
 
   const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
-  int parity = 0;
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t i = tile * kBlock + tid;
     bool active = i < nd;
     if (rnd > 1 && active) active = (hash32(i ^ iter_salt) % (unsigned)rnd) == 0u;
     double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
+    int seed = -1;
     if (active) {
       const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
       const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
+      seed = nn_cache[i];
       xf_apply(xf.X, a.x, a.y, z0, tx, ty, tz);
       xf_apply(xf.Sinv, tx, ty, tz, sx, sy, sz);
     }
     int bj;
     double bd2;
     unsigned boidx;
-    nn_block_search<EXACT>(model, active, sx, sy, sz, maxdist2, sm, parity, bj, bd2, boidx, stage2);
+    nn_warp_search<EXACT>(model, sm, active, sx, sy, sz, maxdist2, seed, bj, bd2, boidx, stage2);
+    if (active) nn_cache[i] = bj;
     if (active && bj >= 0) {
       const double2 pa = __ldg(reinterpret_cast<const double2*>(model.p64 + bj));
       const double pz = __ldg(reinterpret_cast<const double*>(model.p64 + bj) + 2);
@@ -124,14 +127,14 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     }
   }
   block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
-  if (tid == 0 && stage2) atomicAdd(stage2_counter, stage2);
+  if ((tid & 31) == 0 && stage2) atomicAdd(stage2_counter, stage2);
 }
 
 // One block of 384 threads.  Deterministic: 8 interleaved slices per moment, combined in a fixed tree.
 __global__ void __launch_bounds__(384)
 icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials, int nblocks,
                  double* __restrict__ rms_log, unsigned long long* __restrict__ npairs_log,
-                 unsigned* __restrict__ stage2_counter) {
+                 unsigned* __restrict__ stage2_log, unsigned* __restrict__ stage2_counter) {
   if (st->done) return;
   __shared__ double part[NS_MAX][8];
   __shared__ double mom[NS_MAX];
@@ -169,6 +172,7 @@ icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials
   for (int i = 0; i < 16; ++i) st->alignxf[i] = alignxf[i];
   rms_log[st->iters_run] = ret;
   npairs_log[st->iters_run] = (unsigned long long)(np + 0.5);
+  stage2_log[st->iters_run] = st->stage2_last;
   st->iters_run += 1;
   // Scan::transformMatrix (scan.cc:878-898): transMat <- alignxf*transMat, dalignxf <- alignxf*dalignxf
   double tmp[16];
@@ -210,8 +214,7 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
   for (int k = 0; k < 8; ++k) acc[k] = 0.0;
   unsigned stage2 = 0;
   const size_t ntiles = (n + kBlock - 1) / kBlock;
-  int parity = 0;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t i = tile * kBlock + tid;
     const bool active = i < n;
     double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
@@ -222,7 +225,7 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
     int bj;
     double bd2;
     unsigned boidx;
-    nn_block_search<true>(model, active, sx, sy, sz, maxdist2, sm, parity, bj, bd2, boidx, stage2);
+    nn_warp_search<true>(model, sm, active, sx, sy, sz, maxdist2, -1, bj, bd2, boidx, stage2);
     if (active) {
       if (idx_out) idx_out[i] = bj >= 0 ? (int32_t)boidx : -1;
       if (d2_out) d2_out[i] = bj >= 0 ? bd2 : -1.0;

@@ -4,17 +4,27 @@
 // (reference src/slam6d/kd.cc:78-87, include/slam6d/kdTreeImpl.h:345-383): closest model point with
 // squared distance STRICTLY below maxdist2, else none.
 //
-// Two stages, both inside the calling kernel (one launch):
-//   stage 1  one thread per query: the 3x3x3 cell stencil, read as 9 contiguous x-runs of the
-//            cell-sorted fp32x4 point array.  Exact whenever the hit is closer than one cell edge.
-//   stage 2  one warp per still-open query: rows (dy,dz) are visited ring by ring, one row per lane,
-//            each row clipped to the x-extent of the current search sphere; after every 32 rows a
-//            warp-shuffle arg-min merges the lanes and the loop stops as soon as the best distance
-//            is covered by the completed rings.
-// Precision: candidates are screened in fp32 on origin-relative coordinates against a bound that is
-// provably above the fp64 distance of any candidate able to beat the current best; survivors are
-// re-evaluated in fp64 with the reference's Dist2 rounding (no FMA), so EXACT=true returns the fp64
-// arg-min.  EXACT=false takes all decisions in fp32 (fast mode of the fused match).
+// Structure (everything is per thread or per warp -- no block barrier in the query loop):
+//   seed     the neighbour found in the previous ICP iteration gives an exact upper bound r on the
+//            NN distance (the idea of the reference's "cached k-d tree", doc/papers/3dim2007.pdf,
+//            applied to a grid); no seed -> r = maxdist.
+//   stage 1  one thread per query: the cells of the 3x3x3 stencil that the ball of radius r touches,
+//            read as contiguous x-runs of the cell-sorted fp32x4 point array, in ONE flattened loop
+//            (a per-thread range table in shared memory keeps the lanes of a warp busy).
+//            Exact whenever the hit is closer than one cell edge.
+//   stage 1b one thread per query, for balls wider than a cell (early ICP iterations, no seed): the rows
+//            of cells the ball touches are enumerated near-to-far, eight at a time (their ranges are
+//            fetched with independent loads), scanned in the same flattened loop, and the ball shrinks
+//            as soon as a candidate is found.  Covers up to kBallRings rings of cells.
+//   stage 2  (rare: radius beyond kBallRings cells, or an fp32-ambiguous winner) the query is finished by
+//            its own warp: rows (dy,dz) are visited ring by ring, one row per lane, clipped to the
+//            x-extent of the current search sphere; after every 32 rows a warp-shuffle arg-min merges
+//            the lanes and the loop stops as soon as the best distance is covered by the finished rings.
+// Precision: the inner loops run in fp32 on origin-relative coordinates and track the best and the
+// second-best distance.  If the two are separated by more than the provable fp32 error the fp32 winner
+// IS the fp64 arg-min and only its distance is re-evaluated in fp64 (reference Dist2 rounding, no FMA);
+// otherwise (rare) the same cells are rescanned with every contender evaluated in fp64.  EXACT=false
+// skips the fp64 work and takes all decisions in fp32 (fast mode of the fused match).
 #pragma once
 #include "common.cuh"
 
@@ -23,21 +33,25 @@ namespace b200 {
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 constexpr unsigned kNoIdx = 0xFFFFFFFFu;
+constexpr int kMaxRows = 9;
+constexpr int kBallRings = 8;   // thread-level ball scan covers cells up to this Chebyshev distance
 
 struct Best {
   double d2;      // exact (EXACT) or fp32 (fast) squared distance of the current best, init maxdist2
-  float thr;      // fp32 screening bound
+  float thr;      // fp32 screening bound (exact rescans only)
   int j;          // sorted position of the best point, -1 = none
   unsigned oidx;  // its original row
 };
 
+struct Cand {     // fp32 tracking state of the inner loops
+  float d1;       // smallest fp32 distance seen
+  float d2nd;     // second smallest
+  int j1;         // position of the smallest
+};
+
+// thread-private columns: rng[k][tid]
 struct SearchSmem {
-  double sx[kBlock], sy[kBlock], sz[kBlock];
-  double bd2[kBlock];
-  int bj[kBlock];
-  unsigned boidx[kBlock];
-  int list[kBlock];
-  int warp_cnt[2][kWarps];  // double-buffered by call parity (a fast warp may enter the next tile)
+  unsigned rng[2 * kMaxRows][kBlock];
 };
 
 template <bool EXACT>
@@ -50,67 +64,58 @@ __device__ __forceinline__ float filter_bound(double b, float e) {
   return __double2float_ru(t);
 }
 
+// fp32 version of the same error bound: tol(d) >= |d2_fp32 - d2_exact| for a candidate at fp32 distance d
+__device__ __forceinline__ float fp32_tol(float d, float e) {
+  return (e * (4.0f * sqrtf(d) + 4.0f * e)) * 1.01f + 2e-6f * d + 1e-37f;
+}
+
+__device__ __forceinline__ float query_err(float qx, float qy, float qz, float bmax) {
+  const float qm = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+  return 1.25e-7f * (qm + bmax) + 1e-30f;  // > 2.02 * 2^-24 * (|q|+|p|)
+}
+
 __device__ __forceinline__ int cell_coord(double v, double g0, double inv_h) {
   double f = floor((v - g0) * inv_h);
   f = fmin(fmax(f, -1.0e9), 1.0e9);
   return (int)f;
 }
 
-template <bool EXACT>
-__device__ __forceinline__ void scan_range(const GridDev& g, unsigned beg, unsigned end, float qx,
-                                           float qy, float qz, double sx, double sy, double sz,
-                                           float e, Best& b) {
-#pragma unroll 2
+// Dist2(query, point), globals.icc:237-245: (x2-x1)^2 summed left to right, no contraction
+__device__ __forceinline__ double exact_d2(const GridDev& g, int j, double sx, double sy, double sz) {
+  const double2 pa = __ldg(reinterpret_cast<const double2*>(g.p64 + j));
+  const double pz = __ldg(reinterpret_cast<const double*>(g.p64 + j) + 2);
+  const double ex = __dsub_rn(pa.x, sx), ey = __dsub_rn(pa.y, sy), ez = __dsub_rn(pz, sz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+}
+
+__device__ __forceinline__ float dist32(const float4 p, float qx, float qy, float qz) {
+  const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+  return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+__device__ __forceinline__ void cand_update(Cand& c, float d, int j) {
+  c.d2nd = fminf(c.d2nd, fmaxf(d, c.d1));
+  if (d < c.d1) { c.d1 = d; c.j1 = j; }
+}
+
+// exact (slow) scan of one range: every candidate that passes the fp32 screen is evaluated in fp64
+__device__ __forceinline__ void scan_range_exact(const GridDev& g, unsigned beg, unsigned end, float qx,
+                                                 float qy, float qz, double sx, double sy, double sz,
+                                                 float e, Best& b) {
   for (unsigned j = beg; j < end; ++j) {
     const float4 p = __ldg(g.p32 + j);
-    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    const float d2 = dist32(p, qx, qy, qz);
     if (d2 < b.thr) {
       const unsigned oi = __float_as_uint(p.w);
-      if (EXACT) {
-        const double2 pa = __ldg(reinterpret_cast<const double2*>(g.p64 + j));
-        const double pz = __ldg(reinterpret_cast<const double*>(g.p64 + j) + 2);
-        // Dist2(query, point), globals.icc:237-245: (x2-x1)^2 summed left to right, no contraction
-        const double ex = __dsub_rn(pa.x, sx), ey = __dsub_rn(pa.y, sy), ez = __dsub_rn(pz, sz);
-        const double d2e =
-            __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-        if (d2e < b.d2 || (d2e == b.d2 && b.j >= 0 && oi < b.oidx)) {
-          b.d2 = d2e;
-          b.j = (int)j;
-          b.oidx = oi;
-          b.thr = filter_bound<true>(d2e, e);
-        }
-      } else {
-        b.d2 = (double)d2;
-        b.thr = d2;
+      const double d2e = exact_d2(g, (int)j, sx, sy, sz);
+      if (d2e < b.d2 || (d2e == b.d2 && b.j >= 0 && oi < b.oidx)) {
+        b.d2 = d2e;
         b.j = (int)j;
         b.oidx = oi;
+        b.thr = filter_bound<true>(d2e, e);
       }
     }
   }
-}
-
-// stage 1: 27-cell stencil as 9 x-runs
-template <bool EXACT>
-__device__ __forceinline__ void stencil_search(const GridDev& g, int cx, int cy, int cz, float qx,
-                                               float qy, float qz, double sx, double sy, double sz,
-                                               float e, Best& b) {
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-  if (x0 > x1) return;
-  unsigned rb[9], re[9];
-#pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
-    if ((unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz) {
-      const size_t row = ((size_t)z * g.ny + y) * g.nx;
-      rb[r] = __ldg(g.cell_start + row + x0);
-      re[r] = __ldg(g.cell_start + row + x1 + 1);
-    } else {
-      rb[r] = re[r] = 0;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 9; ++r) scan_range<EXACT>(g, rb[r], re[r], qx, qy, qz, sx, sy, sz, e, b);
 }
 
 __device__ __forceinline__ void best_merge(Best& b, double od2, int oj, unsigned ooidx) {
@@ -119,6 +124,159 @@ __device__ __forceinline__ void best_merge(Best& b, double od2, int oj, unsigned
     b.j = oj;
     b.oidx = ooidx;
   }
+}
+
+// ---- stage 1 -------------------------------------------------------------------------------------
+// flattened fp32 scan of the first `nrows` ranges of this thread's table
+__device__ __forceinline__ void scan_rows(const GridDev& g, const SearchSmem& sm, int nrows, float qx,
+                                          float qy, float qz, Cand& c) {
+  const int tid = threadIdx.x;
+  int r = 0;
+  unsigned j = 0, end = 0;
+  for (;;) {
+    if (j >= end) {
+      bool more = false;
+      while (r < nrows) {
+        j = sm.rng[2 * r][tid];
+        end = sm.rng[2 * r + 1][tid];
+        ++r;
+        if (j < end) { more = true; break; }
+      }
+      if (!more) break;
+    }
+    const float d = dist32(__ldg(g.p32 + j), qx, qy, qz);
+    if ((int)j != c.j1) cand_update(c, d, (int)j);   // a point met twice must not become its own runner-up
+    ++j;
+  }
+}
+
+// Turns the fp32 tracking state into the exact result.  Returns false when the winner is ambiguous in
+// fp32 (caller must settle it with an exact rescan).
+template <bool EXACT>
+__device__ __forceinline__ bool finalize_cand(const GridDev& g, const Cand& c, float e, double sx, double sy,
+                                              double sz, Best& b) {
+  if (c.j1 < 0) return true;  // nothing in reach (b keeps its seed / {maxdist2,-1})
+  if (!EXACT) {
+    if (c.j1 != b.j && (double)c.d1 < b.d2) {
+      b.d2 = (double)c.d1; b.j = c.j1; b.oidx = __float_as_uint(__ldg(g.p32 + c.j1).w);
+    }
+    return true;
+  }
+  if (c.d2nd <= c.d1 + 2.5f * fp32_tol(c.d1, e)) return false;
+  if (c.j1 != b.j) {  // a new winner: it is the fp64 arg-min of everything scanned plus the seed
+    const double d2e = exact_d2(g, c.j1, sx, sy, sz);
+    if (d2e < b.d2) { b.d2 = d2e; b.j = c.j1; b.oidx = __float_as_uint(__ldg(g.p32 + c.j1).w); }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void cand_seed(const GridDev& g, const Best& b, float qx, float qy, float qz, Cand& c) {
+  c.d1 = 3.0e38f; c.d2nd = 3.0e38f; c.j1 = -1;
+  // the seed point itself, measured the same way as every candidate
+  if (b.j >= 0) { c.d1 = dist32(__ldg(g.p32 + b.j), qx, qy, qz); c.j1 = b.j; }
+}
+
+// Searches the part of the 3x3x3 stencil that the ball (s, b.d2) touches.  `b` enters with the seed
+// (or {maxdist2, -1}) and leaves with the exact best inside that region.
+template <bool EXACT>
+__device__ __forceinline__ void stencil_search(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz,
+                                               float fx, float fy, float fz, float qx, float qy, float qz,
+                                               double sx, double sy, double sz, float e, Best& b) {
+  const int tid = threadIdx.x;
+  const float h = (float)g.h;
+  const float hh = h * h;
+  const float r2 = fminf(__double2float_ru(b.d2), 3.0e38f) * 1.00001f + 1e-6f * hh;
+  const float lo_y = fy * fy, hi_y = (h - fy) * (h - fy);
+  const float lo_z = fz * fz, hi_z = (h - fz) * (h - fz);
+  const float lo_x = fx * fx, hi_x = (h - fx) * (h - fx);
+  int nrows = 0;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int dy = (r % 3) - 1, dz = (r / 3) - 1;
+    const int y = cy + dy, z = cz + dz;
+    const float rem = r2 - (dy < 0 ? lo_y : (dy > 0 ? hi_y : 0.f)) - (dz < 0 ? lo_z : (dz > 0 ? hi_z : 0.f));
+    const int x0 = max(cx - (lo_x <= rem ? 1 : 0), 0);
+    const int x1 = min(cx + (hi_x <= rem ? 1 : 0), g.nx - 1);
+    if (rem >= 0.f && (unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz && x0 <= x1) {
+      const size_t row = ((size_t)z * g.ny + y) * g.nx;
+      sm.rng[2 * nrows][tid] = __ldg(g.cell_start + row + x0);
+      sm.rng[2 * nrows + 1][tid] = __ldg(g.cell_start + row + x1 + 1);
+      ++nrows;
+    }
+  }
+  Cand c;
+  cand_seed(g, b, qx, qy, qz, c);
+  scan_rows(g, sm, nrows, qx, qy, qz, c);
+  if (finalize_cand<EXACT>(g, c, e, sx, sy, sz, b)) return;
+  // rare: two contenders closer than the fp32 error -> settle in fp64 (ties: lowest original row)
+  b.thr = filter_bound<true>(b.d2, e);
+  for (int k = 0; k < nrows; ++k)
+    scan_range_exact(g, sm.rng[2 * k][tid], sm.rng[2 * k + 1][tid], qx, qy, qz, sx, sy, sz, e, b);
+}
+
+// ---- stage 1b ------------------------------------------------------------------------------------
+__device__ __forceinline__ int zigzag(int t) { return (t & 1) ? -((t + 1) >> 1) : (t >> 1); }  // 0,-1,1,-2,2
+// distance from a query at offset f inside its cell to the slab of cells d cells away (d != 0)
+__device__ __forceinline__ float slab_dist(int d, float f, float h) {
+  return d > 0 ? (float)d * h - f : (d < 0 ? f + (float)(-d - 1) * h : 0.f);
+}
+
+// Thread-level exact search of the ball (s, b.d2) when it is wider than a cell: covers the cells within
+// `kmax` (<= kBallRings) of the query's cell.  Returns false if the fp32 winner is ambiguous.
+template <bool EXACT>
+__device__ __forceinline__ bool ball_scan(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz, float fx,
+                                          float fy, float fz, float qx, float qy, float qz, double sx,
+                                          double sy, double sz, float e, int kmax, Best& b) {
+  const int tid = threadIdx.x;
+  const float h = (float)g.h, inv_h = (float)g.inv_h;
+  const float hh = h * h;
+  float r2 = fminf(__double2float_ru(b.d2), 3.0e38f) * 1.00001f + 1e-6f * hh;
+  Cand c;
+  cand_seed(g, b, qx, qy, qz, c);
+  int tz = 0, ty = 0;
+  bool exhausted = false;
+  while (!exhausted) {
+    // ---- gather the cell-table indices of up to 8 rows the ball touches, nearest slabs first
+    int n = 0;
+    while (n < 8) {
+      if (tz > 2 * kmax) { exhausted = true; break; }
+      const int dz = zigzag(tz);
+      const float ddz = slab_dist(dz, fz, h);
+      const float remz = r2 - ddz * ddz;
+      if (remz < 0.f || ty > 2 * kmax) { ++tz; ty = 0; continue; }
+      const int dy = zigzag(ty);
+      ++ty;
+      const float ddy = slab_dist(dy, fy, h);
+      const float rem = remz - ddy * ddy;
+      const int y = cy + dy, z = cz + dz;
+      if (rem < 0.f || (unsigned)y >= (unsigned)g.ny || (unsigned)z >= (unsigned)g.nz) continue;
+      const float w = sqrtf(rem) * 1.00001f + 1e-6f * h;
+      const int x0 = max(cx + (int)floorf((fx - w) * inv_h), 0);
+      const int x1 = min(cx + (int)floorf((fx + w) * inv_h), g.nx - 1);
+      if (x0 > x1) continue;
+      const unsigned row = (unsigned)(((size_t)z * g.ny + y) * g.nx);
+      sm.rng[2 * n][tid] = row + (unsigned)x0;
+      sm.rng[2 * n + 1][tid] = row + (unsigned)x1 + 1u;
+      ++n;
+    }
+    // ---- resolve them with independent loads
+    unsigned va[8], vb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      va[k] = 0; vb[k] = 0;
+      if (k < n) {
+        va[k] = __ldg(g.cell_start + sm.rng[2 * k][tid]);
+        vb[k] = __ldg(g.cell_start + sm.rng[2 * k + 1][tid]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n) { sm.rng[2 * k][tid] = va[k]; sm.rng[2 * k + 1][tid] = vb[k]; }
+    scan_rows(g, sm, n, qx, qy, qz, c);
+    // ---- shrink the ball to the (error-inflated) fp32 distance of the current best
+    if (c.j1 >= 0) r2 = fminf(r2, (c.d1 + fp32_tol(c.d1, e)) * 1.00001f + 1e-6f * hh);
+  }
+  return finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
 }
 
 // ring index r of flattened row f: f == 0 -> 0, else (2r-1)^2 <= f < (2r+1)^2
@@ -130,24 +288,26 @@ __device__ __forceinline__ int ring_of(long long f) {
   return r;
 }
 
-// stage 2: whole warp works on one query.  `b` enters identical on all lanes and leaves identical.
+// ---- stage 2 -------------------------------------------------------------------------------------
+// Whole warp works on one query.  `b` enters identical on all lanes and leaves identical.
 template <bool EXACT>
 __device__ __forceinline__ void ring_search_warp(const GridDev& g, int cx, int cy, int cz, float qx,
                                                  float qy, float qz, double sx, double sy,
                                                  double sz, float e, Best& b) {
   const int lane = threadIdx.x & 31;
-  const double fy = (sy - g.g0[1]) - (double)cy * g.h;  // offset of the query inside its cell
-  const double fz = (sz - g.g0[2]) - (double)cz * g.h;
-  const long long kgrid =
-      max(max((long long)cy, (long long)g.ny - 1 - cy), max((long long)cz, (long long)g.nz - 1 - cz));
+  // rings are laid around the in-grid cell nearest to the query, so a query outside the grid does not
+  // walk rings of non-existent rows; row distances are measured from the true query position.
+  const int ccy = min(max(cy, 0), g.ny - 1), ccz = min(max(cz, 0), g.nz - 1);
+  const long long kgrid = max(max(ccy, g.ny - 1 - ccy), max(ccz, g.nz - 1 - ccz));
   for (long long base = 0;; base += 32) {
     const double R = sqrt(b.d2);
-    long long k = (long long)fmin(ceil(R * g.inv_h), 1.0e9);
+    long long k = (long long)fmin(ceil(R * g.inv_h) + (double)(abs(cy - ccy) + abs(cz - ccz) > 0 ? 1 : 0), 1.0e9);
     if (k > kgrid) k = kgrid;
     if (k < 0) k = 0;
     const long long total = (2 * k + 1) * (2 * k + 1);
     if (base >= total) break;
     const long long f = base + lane;
+    unsigned beg = 0, end = 0;
     if (f < total) {
       const int r = ring_of(f);
       int dy = 0, dz = 0;
@@ -159,34 +319,67 @@ __device__ __forceinline__ void ring_search_warp(const GridDev& g, int cx, int c
         else if (side == 2) { dy = r - off; dz = r; }
         else { dy = -r; dz = r - off; }
       }
-      const int y = cy + dy, z = cz + dz;
+      const int y = ccy + dy, z = ccz + dz;
       if ((unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz) {
-        // exact lower bound of the (y,z)-distance between the query and any point of this row
-        const double ddy = dy > 0 ? (double)dy * g.h - fy : (dy < 0 ? fy + (double)(-dy - 1) * g.h : 0.0);
-        const double ddz = dz > 0 ? (double)dz * g.h - fz : (dz < 0 ? fz + (double)(-dz - 1) * g.h : 0.0);
-        const double dyz2 = (ddy > 0 ? ddy * ddy : 0.0) + (ddz > 0 ? ddz * ddz : 0.0);
+        // lower bound of the (y,z)-distance between the query and the slab of cells of this row
+        const double ylo = g.g0[1] + (double)y * g.h, zlo = g.g0[2] + (double)z * g.h;
+        const double ddy = fmax(fmax(ylo - sy, sy - (ylo + g.h)), 0.0);
+        const double ddz = fmax(fmax(zlo - sz, sz - (zlo + g.h)), 0.0);
+        const double dyz2 = ddy * ddy + ddz * ddz;
         if (dyz2 * (1.0 - 1e-9) < b.d2) {
           const double w = sqrt(fmax(b.d2 - dyz2 * (1.0 - 1e-9), 0.0)) * (1.0 + 1e-9) + 1e-300;
           const int x0 = max(cell_coord(sx - w, g.g0[0], g.inv_h), 0);
           const int x1 = min(cell_coord(sx + w, g.g0[0], g.inv_h), g.nx - 1);
           if (x0 <= x1) {
             const size_t row = ((size_t)z * g.ny + y) * g.nx;
-            const unsigned beg = __ldg(g.cell_start + row + x0);
-            const unsigned end = __ldg(g.cell_start + row + x1 + 1);
-            scan_range<EXACT>(g, beg, end, qx, qy, qz, sx, sy, sz, e, b);
+            beg = __ldg(g.cell_start + row + x0);
+            end = __ldg(g.cell_start + row + x1 + 1);
           }
         }
       }
     }
-    // warp arg-min (distance, then original row)
+    // fp32 pass over this lane's row
+    Cand c;
+    c.d1 = 3.0e38f; c.d2nd = 3.0e38f; c.j1 = -1;
+    for (unsigned j = beg; j < end; ++j) cand_update(c, dist32(__ldg(g.p32 + j), qx, qy, qz), (int)j);
+    // warp arg-min of d1 and the runner-up
+    float m1 = c.d1;
+    int mj = c.j1, ml = lane;
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
-      const double od2 = __shfl_xor_sync(0xffffffffu, b.d2, m);
-      const int oj = __shfl_xor_sync(0xffffffffu, b.j, m);
-      const unsigned oo = __shfl_xor_sync(0xffffffffu, b.oidx, m);
-      best_merge(b, od2, oj, oo);
+      const float od = __shfl_xor_sync(0xffffffffu, m1, m);
+      const int oj = __shfl_xor_sync(0xffffffffu, mj, m);
+      const int ol = __shfl_xor_sync(0xffffffffu, ml, m);
+      if (od < m1 || (od == m1 && ol < ml)) { m1 = od; mj = oj; ml = ol; }
     }
-    b.thr = filter_bound<EXACT>(b.d2, e);
+    if (mj >= 0 && m1 < filter_bound<EXACT>(b.d2, e)) {  // the batch may improve the best
+      if (!EXACT) {
+        if ((double)m1 < b.d2) { b.d2 = (double)m1; b.j = mj; b.oidx = __float_as_uint(__ldg(g.p32 + mj).w); }
+      } else {
+        float m2 = lane == ml ? c.d2nd : c.d1;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, m));
+        if (m2 > m1 + 2.5f * fp32_tol(m1, e)) {
+          const double d2e = exact_d2(g, mj, sx, sy, sz);  // same address on all lanes
+          const unsigned oi = __float_as_uint(__ldg(g.p32 + mj).w);
+          if (d2e < b.d2 || (d2e == b.d2 && b.j >= 0 && oi < b.oidx)) { b.d2 = d2e; b.j = mj; b.oidx = oi; }
+        } else {
+          // contenders within the fp32 error: every lane rescans its row in fp64, then merge
+          Best lb = b;
+          lb.thr = filter_bound<true>(b.d2, e);
+          scan_range_exact(g, beg, end, qx, qy, qz, sx, sy, sz, e, lb);
+          if (lb.j < 0) lb.oidx = kNoIdx;
+#pragma unroll
+          for (int m = 16; m > 0; m >>= 1) {
+            const double od2 = __shfl_xor_sync(0xffffffffu, lb.d2, m);
+            const int oj = __shfl_xor_sync(0xffffffffu, lb.j, m);
+            const unsigned oo = __shfl_xor_sync(0xffffffffu, lb.oidx, m);
+            best_merge(lb, od2, oj, oo);
+          }
+          b.d2 = lb.d2; b.j = lb.j; b.oidx = lb.j >= 0 ? lb.oidx : kNoIdx;
+        }
+      }
+    }
     if (b.j >= 0) {
       // rings 0..rc are complete after base+32 rows
       const long long rows_done = base + 32;
@@ -200,79 +393,81 @@ __device__ __forceinline__ void ring_search_warp(const GridDev& g, int cx, int c
   }
 }
 
-// Block-wide search: every thread of a kBlock-thread block calls this once per tile (it contains
-// __syncthreads).  `active` threads carry a query s (in the grid's frame).
+// Warp-synchronous search: every lane of every warp calls this once per tile (it contains warp
+// collectives, no block barrier).  `active` lanes carry a query s (in the grid's frame); seed_j is the
+// sorted position of the neighbour found for this query last time (-1: none).
 template <bool EXACT>
-__device__ __forceinline__ void nn_block_search(const GridDev& g, bool active, double sx, double sy,
-                                                double sz, double maxdist2, SearchSmem& sm,
-                                                int parity, int& out_j, double& out_d2,
-                                                unsigned& out_oidx, unsigned& stage2_count) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm, bool active, double sx,
+                                               double sy, double sz, double maxdist2, int seed_j,
+                                               int& out_j, double& out_d2, unsigned& out_oidx,
+                                               unsigned& stage2_count) {
+  const int lane = threadIdx.x & 31;
   Best b;
   b.d2 = maxdist2;
   b.j = -1;
   b.oidx = kNoIdx;
   b.thr = 0.f;
   bool need2 = false;
+  float qx = 0.f, qy = 0.f, qz = 0.f, e = 0.f;
+  int cx = 0, cy = 0, cz = 0;
   if (active) {
     const double ox = fmax(fmax(g.bbox_lo[0] - sx, sx - g.bbox_hi[0]), 0.0);
     const double oy = fmax(fmax(g.bbox_lo[1] - sy, sy - g.bbox_hi[1]), 0.0);
     const double oz = fmax(fmax(g.bbox_lo[2] - sz, sz - g.bbox_hi[2]), 0.0);
     const double dbox2 = ox * ox + oy * oy + oz * oz;
     if (dbox2 < maxdist2) {  // false for NaN queries as well
-      const double rx = sx - g.c[0], ry = sy - g.c[1], rz = sz - g.c[2];
-      const float qx = (float)rx, qy = (float)ry, qz = (float)rz;
-      const float qm = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
-      const float e = 1.25e-7f * (qm + g.bmax) + 1e-30f;  // > 2.02 * 2^-24 * (|q|+|p|)
-      b.thr = filter_bound<EXACT>(maxdist2, e);
-      const int cx = cell_coord(sx, g.g0[0], g.inv_h);
-      const int cy = cell_coord(sy, g.g0[1], g.inv_h);
-      const int cz = cell_coord(sz, g.g0[2], g.inv_h);
-      stencil_search<EXACT>(g, cx, cy, cz, qx, qy, qz, sx, sy, sz, e, b);
+      qx = (float)(sx - g.c[0]); qy = (float)(sy - g.c[1]); qz = (float)(sz - g.c[2]);
+      e = query_err(qx, qy, qz, g.bmax);
+      cx = cell_coord(sx, g.g0[0], g.inv_h);
+      cy = cell_coord(sy, g.g0[1], g.inv_h);
+      cz = cell_coord(sz, g.g0[2], g.inv_h);
+      // offsets of the query inside its cell (meaningful also for queries outside the grid)
+      const float fx = (float)((sx - g.g0[0]) - (double)cx * g.h);
+      const float fy = (float)((sy - g.g0[1]) - (double)cy * g.h);
+      const float fz = (float)((sz - g.g0[2]) - (double)cz * g.h);
+      if (seed_j >= 0 && (unsigned)seed_j < g.n) {
+        const double ds = EXACT ? exact_d2(g, seed_j, sx, sy, sz)
+                                : (double)dist32(__ldg(g.p32 + seed_j), qx, qy, qz);
+        if (ds < maxdist2) { b.d2 = ds; b.j = seed_j; b.oidx = __float_as_uint(__ldg(g.p32 + seed_j).w); }
+      }
       const double rg2 = g.h * g.h * (1.0 - 1e-9);
-      need2 = !((b.j >= 0 && b.d2 <= rg2) || (maxdist2 <= rg2));
+      if (b.d2 <= rg2) {
+        // the ball fits inside the stencil's guaranteed radius: stage 1 alone is exact
+        stencil_search<EXACT>(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, sx, sy, sz, e, b);
+      } else {
+        const double kneed = ceil(sqrt(b.d2) * g.inv_h);
+        const int kmax = (int)fmin(kneed, (double)kBallRings);
+        const Best seed = b;
+        const bool settled = ball_scan<EXACT>(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, sx, sy, sz, e, kmax, b);
+        const double cover = (double)kmax * g.h;
+        if (!settled) { b = seed; need2 = true; }                       // fp32-ambiguous winner
+        else if (kneed > (double)kBallRings)                            // ball wider than the scan covers
+          need2 = !(b.j >= 0 && b.d2 <= cover * cover * (1.0 - 1e-9));
+      }
     }
   }
-  const unsigned ball = __ballot_sync(0xffffffffu, need2);
-  if (lane == 0) sm.warp_cnt[parity & 1][warp] = __popc(ball);
-  __syncthreads();
-  int offset = 0, nlist = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; ++w) {
-    const int c = sm.warp_cnt[parity & 1][w];
-    if (w < warp) offset += c;
-    nlist += c;
-  }
-  if (nlist > 0) {  // block-uniform
-    if (need2) {
-      const int slot = offset + __popc(ball & ((1u << lane) - 1u));
-      sm.list[slot] = tid;
-      sm.sx[tid] = sx; sm.sy[tid] = sy; sm.sz[tid] = sz;
-      sm.bd2[tid] = b.d2; sm.bj[tid] = b.j; sm.boidx[tid] = b.oidx;
-    }
-    __syncthreads();
-    for (int li = warp; li < nlist; li += kWarps) {
-      const int t = sm.list[li];
-      const double qsx = sm.sx[t], qsy = sm.sy[t], qsz = sm.sz[t];
-      Best wb;
-      wb.d2 = sm.bd2[t]; wb.j = sm.bj[t]; wb.oidx = sm.boidx[t];
-      const float qx = (float)(qsx - g.c[0]), qy = (float)(qsy - g.c[1]), qz = (float)(qsz - g.c[2]);
-      const float qm = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
-      const float e = 1.25e-7f * (qm + g.bmax) + 1e-30f;
-      wb.thr = filter_bound<EXACT>(wb.d2, e);
-      const int cx = cell_coord(qsx, g.g0[0], g.inv_h);
-      const int cy = cell_coord(qsy, g.g0[1], g.inv_h);
-      const int cz = cell_coord(qsz, g.g0[2], g.inv_h);
-      ring_search_warp<EXACT>(g, cx, cy, cz, qx, qy, qz, qsx, qsy, qsz, e, wb);
-      if (lane == 0) { sm.bd2[t] = wb.d2; sm.bj[t] = wb.j; sm.boidx[t] = wb.oidx; }
-    }
-    __syncthreads();
-    if (need2) { b.d2 = sm.bd2[tid]; b.j = sm.bj[tid]; b.oidx = sm.boidx[tid]; }
-    if (tid == 0) stage2_count += (unsigned)nlist;
+  unsigned todo = __ballot_sync(0xffffffffu, need2);
+  stage2_count += lane == 0 ? __popc(todo) : 0;
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    Best wb;
+    wb.d2 = __shfl_sync(0xffffffffu, b.d2, src);
+    wb.j = __shfl_sync(0xffffffffu, b.j, src);
+    wb.oidx = __shfl_sync(0xffffffffu, b.oidx, src);
+    wb.thr = 0.f;
+    const double wsx = __shfl_sync(0xffffffffu, sx, src), wsy = __shfl_sync(0xffffffffu, sy, src),
+                 wsz = __shfl_sync(0xffffffffu, sz, src);
+    const float wqx = __shfl_sync(0xffffffffu, qx, src), wqy = __shfl_sync(0xffffffffu, qy, src),
+                wqz = __shfl_sync(0xffffffffu, qz, src), we = __shfl_sync(0xffffffffu, e, src);
+    const int wcx = __shfl_sync(0xffffffffu, cx, src), wcy = __shfl_sync(0xffffffffu, cy, src),
+              wcz = __shfl_sync(0xffffffffu, cz, src);
+    ring_search_warp<EXACT>(g, wcx, wcy, wcz, wqx, wqy, wqz, wsx, wsy, wsz, we, wb);
+    if (lane == src) { b.d2 = wb.d2; b.j = wb.j; b.oidx = wb.oidx; }
   }
   out_j = b.j;
   out_d2 = b.d2;
-  out_oidx = b.oidx;
+  out_oidx = b.j >= 0 ? b.oidx : kNoIdx;
 }
 
 }  // namespace b200

@@ -156,6 +156,11 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
                   const b200icp_match_params* params, double* rms_per_iter,
                   uint64_t* npairs_per_iter, b200icp_match_result* result);
 
+/* Per-iteration record of the context's last b200icp_match: device time of the correspondence kernel
+ * and of the solve kernel (ms; zeros unless params.profile was set) and the number of queries that
+ * needed the wide ring search.  Returns the number of iterations recorded (may exceed cap). */
+int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2);
+
 /* ---- normals --------------------------------------------------------------------------------
  * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):
  * exact k nearest neighbours (the point itself included), PCA, smallest-eigenvalue eigenvector,
