@@ -73,7 +73,7 @@ def _load():
         "b200icp_nn_batch_device": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
         "b200icp_align_pairs": (i32, [i32, sz, dp, dp, dp, dp, dp, dp, C.POINTER(f64)]),
         "b200icp_match": (i32, [vp, vp, vp, C.POINTER(MatchParams), dp, dp, C.POINTER(MatchResult)]),
-        "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp]),
+        "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
         "b200icp_euler_to_matrix4": (None, [dp, dp, dp]),
@@ -293,9 +293,9 @@ class icp6D:
         k = res.iterations_run
         prof = None
         if k > 0:
-            nn, sv, s2 = np.zeros(k), np.zeros(k), np.zeros(k, dtype=np.uint32)
-            lib.b200icp_last_profile(self.ctx._h, k, _ptr(nn), _ptr(sv), _ptr(s2))
-            prof = {"nn_ms": nn, "solve_ms": sv, "stage2": s2}
+            nn, sv, s2, se = np.zeros(k), np.zeros(k), np.zeros(k, dtype=np.uint32), np.zeros(k, dtype=np.uint32)
+            lib.b200icp_last_profile(self.ctx._h, k, _ptr(nn), _ptr(sv), _ptr(s2), _ptr(se))
+            prof = {"nn_ms": nn, "solve_ms": sv, "stage2": s2, "searches": se}
         return {"profile": prof, "iterations": res.iterations, "iterations_run": k, "rms": rms[:k].copy(),
                 "npairs": npairs[:k].copy(), "result": res}
 

@@ -80,6 +80,7 @@ struct b200icp_ctx {
   DevBuf<unsigned> stage2_counter;
   DevBuf<unsigned> stage2_log;
   DevBuf<int> nn_cache;             // per data point: neighbour of the previous iteration
+  DevBuf<float> nn_budget;          // per data point: motion budget left before it must search again
   std::vector<double> prof_nn_ms, prof_solve_ms;   // last profiled match, per iteration
   std::vector<unsigned> prof_stage2;
   DevBuf<double> d_small;           // 64 doubles of scratch (transforms for API kernels)
@@ -119,12 +120,17 @@ double cells_for(const double ext[3], double h, int dims[3]) {
 }
 
 template <bool NAPX, bool PLANE, bool EXACT>
-void launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const b200icp_scan* data,
-                 double maxdist2, int rnd, int* grid_out) {
+cudaError_t launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const b200icp_scan* data,
+                        double maxdist2, int rnd, int* grid_out) {
   auto kern = icp_iter_kernel<NAPX, PLANE, EXACT>;
+  constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
+  const size_t smem = sizeof(IterSmem<NS>);
   if (ctx->blocks_per_sm[variant] == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kBlock, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kBlock, smem);
+    if (e != cudaSuccess) return e;
     ctx->blocks_per_sm[variant] = std::max(b, 1);
   }
   const uint32_t nd = (uint32_t)data->n;
@@ -132,25 +138,28 @@ void launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const
   const int grid = (int)std::min<uint32_t>(
       ntiles, (uint32_t)(ctx->sm_count * std::min(ctx->blocks_per_sm[variant], kMaxBlocksPerSm)));
   *grid_out = grid;
-  kern<<<grid, kBlock, 0, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p,
-                                         maxdist2, rnd, ctx->nn_cache.p, ctx->partials.p,
-                                         ctx->stage2_counter.p);
+  kern<<<grid, kBlock, smem, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p,
+                                            maxdist2, rnd, ctx->nn_cache.p, ctx->nn_budget.p, ctx->partials.p,
+                                            ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p,
+                                            ctx->stage2_log.p);
+  return cudaSuccess;
 }
 
 int launch_iter_dispatch(b200icp_ctx* ctx, bool napx, bool plane, bool exact,
                          const b200icp_scan* model, const b200icp_scan* data, double maxdist2,
                          int rnd, int* grid_out) {
   const int v = (napx ? 4 : 0) | (plane ? 2 : 0) | (exact ? 1 : 0);
+  cudaError_t e;
   switch (v) {
-    case 0: launch_iter<false, false, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 1: launch_iter<false, false, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 2: launch_iter<false, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 3: launch_iter<false, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 6: launch_iter<true, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 7: launch_iter<true, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 0: e = launch_iter<false, false, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 1: e = launch_iter<false, false, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 2: e = launch_iter<false, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 3: e = launch_iter<false, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 6: e = launch_iter<true, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 7: e = launch_iter<true, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
     default: return -1;
   }
-  return 0;
+  return e == cudaSuccess ? 0 : -2;
 }
 
 int max_iter_grid(const b200icp_ctx* ctx) { return ctx->sm_count * kMaxBlocksPerSm; }
@@ -220,6 +229,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
   ctx->stage2_counter.release();
   ctx->stage2_log.release();
   ctx->nn_cache.release();
+  ctx->nn_budget.release();
   ctx->d_small.release();
   if (ctx->own) cudaStreamDestroy(ctx->own);
   delete ctx;
@@ -578,12 +588,14 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   }
   CU_TRY(ctx->rms_log.ensure((size_t)max_iter));
   CU_TRY(ctx->npairs_log.ensure((size_t)max_iter));
-  CU_TRY(ctx->stage2_log.ensure((size_t)max_iter));
+  CU_TRY(ctx->stage2_log.ensure(2 * (size_t)max_iter));
   CU_TRY(ctx->nn_cache.ensure(data->n));
+  CU_TRY(ctx->nn_budget.ensure(data->n));
 
   IterState* hs = ctx->h_state;
   memset(hs, 0, sizeof(IterState));
   memcpy(hs->X, data->dalignxf, sizeof hs->X);
+  memcpy(hs->Xprev, data->dalignxf, sizeof hs->Xprev);
   memcpy(hs->T, data->transMat, sizeof hs->T);
   memcpy(hs->S, model->dalignxf, sizeof hs->S);
   m4_inverse(hs->S, hs->Sinv);
@@ -596,6 +608,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   hs->max_iter = max_iter;
   CU_TRY(cudaMemcpyAsync(ctx->d_state.p, hs, sizeof(IterState), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(ctx->nn_cache.p, 0xFF, data->n * sizeof(int), st));  // -1: no cached neighbour
+  CU_TRY(cudaMemsetAsync(ctx->nn_budget.p, 0, data->n * sizeof(float), st));
 
   const double maxdist2 = prm->max_dist_match * prm->max_dist_match;
   const bool exact = prm->exact != 0;
@@ -623,11 +636,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
       if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i], st));
       if (launch_iter_dispatch(ctx, napx, plane, exact, model, data, maxdist2, prm->rnd, &grid) != 0)
         return fail(B200ICP_EINVAL, "match: unsupported kernel variant");
-      if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i + 1], st));
-      icp_solve_kernel<<<1, 384, 0, st>>>(ctx->d_state.p, ctx->partials.p, grid, ctx->rms_log.p,
-                                          ctx->npairs_log.p, ctx->stage2_log.p, ctx->stage2_counter.p);
-      if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
-      launches += 2;
+      if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 1], st)); CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
+      launches += 1;
     }
     launched += todo;
     CU_TRY(cudaGetLastError());
@@ -662,8 +672,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   }
   ctx->prof_nn_ms.clear(); ctx->prof_solve_ms.clear(); ctx->prof_stage2.clear();
   if (fin.iters_run > 0) {
-    ctx->prof_stage2.resize(fin.iters_run);
-    CU_TRY(cudaMemcpy(ctx->prof_stage2.data(), ctx->stage2_log.p, fin.iters_run * sizeof(unsigned),
+    ctx->prof_stage2.resize(2 * (size_t)fin.iters_run);
+    CU_TRY(cudaMemcpy(ctx->prof_stage2.data(), ctx->stage2_log.p, 2 * (size_t)fin.iters_run * sizeof(unsigned),
                       cudaMemcpyDeviceToHost));
   }
   if (profile && ev_i >= 3) {
@@ -686,13 +696,15 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   return B200ICP_OK;
 }
 
-int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2) {
+int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2,
+                         uint32_t* searches) {
   if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
-  const int n = (int)ctx->prof_stage2.size();
+  const int n = (int)(ctx->prof_stage2.size() / 2);
   for (int i = 0; i < n && i < cap; ++i) {
     if (nn_ms) nn_ms[i] = i < (int)ctx->prof_nn_ms.size() ? ctx->prof_nn_ms[i] : 0.0;
     if (solve_ms) solve_ms[i] = i < (int)ctx->prof_solve_ms.size() ? ctx->prof_solve_ms[i] : 0.0;
-    if (stage2) stage2[i] = ctx->prof_stage2[i];
+    if (stage2) stage2[i] = ctx->prof_stage2[2 * i];
+    if (searches) searches[i] = ctx->prof_stage2[2 * i + 1];
   }
   return n;
 }

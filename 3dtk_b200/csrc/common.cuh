@@ -35,6 +35,7 @@ struct GridDev {
 // Scan::dalignxf, src/slam6d/scan.cc:878-898).
 struct IterState {
   double X[16];       // data scan dalignxf   (current = X * original)
+  double Xprev[16];   // X before the last alignxf (motion of each query since the previous iteration)
   double T[16];       // data scan transMat
   double S[16];       // model scan dalignxf  (Source->dalignxf, scan.cc:1240)
   double Sinv[16];    // M4inv(S)             (searchTree.cc:109-110)

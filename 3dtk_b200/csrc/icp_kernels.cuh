@@ -17,7 +17,7 @@
 namespace b200 {
 
 struct XfSmem {
-  double X[16], Sinv[16], S[16], Nm[9], o[3];
+  double X[16], Xprev[16], Sinv[16], S[16], Nm[9], o[3];
 };
 
 __device__ __forceinline__ void xf_apply(const double* M, double x, double y, double z, double& ox,
@@ -41,9 +41,35 @@ __device__ __forceinline__ unsigned hash32(unsigned x) {
   return x;
 }
 
-template <int NS>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double* __restrict__ out) {
+// thread-private accumulator column in shared memory: element k of this thread lives at base[k*kBlock]
+struct SmemAcc {
+  double* base;
+  __device__ __forceinline__ double& operator[](int k) const { return base[k * kBlock]; }
+};
+
+template <int NS, class Acc>
+__device__ __forceinline__ void block_reduce_store(Acc acc, double* __restrict__ out) {
   __shared__ double red[kWarps][NS_MAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+  for (int k = 0; k < NS; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double v = red[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) v += red[w][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ void block_reduce_store_regs(double (&acc)[NS], double* __restrict__ out) {
+  __shared__ double red[kWarps][NS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
@@ -61,95 +87,26 @@ __device__ __forceinline__ void block_reduce_store(double (&acc)[NS], double* __
   }
 }
 
-template <bool NAPX, bool PLANE, bool EXACT>
-__global__ void __launch_bounds__(kBlock, 2)
-icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __restrict__ dn,
-                uint32_t nd, const IterState* __restrict__ st, double maxdist2, int rnd,
-                int* __restrict__ nn_cache, double* __restrict__ partials,
-                unsigned* __restrict__ stage2_counter) {
-  if (st->done) return;
-  constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
-  __shared__ SearchSmem sm;
-  __shared__ XfSmem xf;
-  const int tid = threadIdx.x;
-  if (tid < 16) { xf.X[tid] = st->X[tid]; xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid]; }
-  if (tid < 9) xf.Nm[tid] = st->Nm[tid];
-  if (tid < 3) xf.o[tid] = st->o[tid];
-  const unsigned iter_salt = (unsigned)st->iter * 0x9E3779B9u;
-  __syncthreads();
-
-  double acc[NS];
-#pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
-  unsigned stage2 = 0;
-
-  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t i = tile * kBlock + tid;
-    bool active = i < nd;
-    if (rnd > 1 && active) active = (hash32(i ^ iter_salt) % (unsigned)rnd) == 0u;
-    double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
-    int seed = -1;
-    if (active) {
-      const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
-      const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
-      seed = nn_cache[i];
-      xf_apply(xf.X, a.x, a.y, z0, tx, ty, tz);
-      xf_apply(xf.Sinv, tx, ty, tz, sx, sy, sz);
-    }
-    int bj;
-    double bd2;
-    unsigned boidx;
-    nn_warp_search<EXACT>(model, sm, active, sx, sy, sz, maxdist2, seed, bj, bd2, boidx, stage2);
-    if (active) nn_cache[i] = bj;
-    if (active && bj >= 0) {
-      const double2 pa = __ldg(reinterpret_cast<const double2*>(model.p64 + bj));
-      const double pz = __ldg(reinterpret_cast<const double*>(model.p64 + bj) + 2);
-      double p1[3], p2[3] = {tx, ty, tz};
-      xf_apply(xf.S, pa.x, pa.y, pz, p1[0], p1[1], p1[2]);
-      double nv[3] = {0, 0, 0};
-      if (PLANE) {
-        const double2 na = __ldg(reinterpret_cast<const double2*>(dn + i));
-        const double n2 = __ldg(reinterpret_cast<const double*>(dn + i) + 2);
-        nv[0] = xf.Nm[0] * na.x + xf.Nm[1] * na.y + xf.Nm[2] * n2;
-        nv[1] = xf.Nm[3] * na.x + xf.Nm[4] * na.y + xf.Nm[5] * n2;
-        nv[2] = xf.Nm[6] * na.x + xf.Nm[7] * na.y + xf.Nm[8] * n2;
-        const double nl = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);  // Normalize3
-        nv[0] /= nl; nv[1] /= nl; nv[2] /= nl;
-        // s <- (n.(s-t)) n + t   (searchTree.cc:149-162)
-        const double dot = nv[0] * (p1[0] - p2[0]) + nv[1] * (p1[1] - p2[1]) + nv[2] * (p1[2] - p2[2]);
-        p1[0] = nv[0] * dot + p2[0];
-        p1[1] = nv[1] * dot + p2[1];
-        p1[2] = nv[2] * dot + p2[2];
-      }
-      if (NAPX) accumulate_napx(acc, p1, p2, nv, xf.o);
-      else accumulate_p2p(acc, p1, p2, xf.o);
-    }
-  }
-  block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
-  if ((tid & 31) == 0 && stage2) atomicAdd(stage2_counter, stage2);
-}
-
-// One block of 384 threads.  Deterministic: 8 interleaved slices per moment, combined in a fixed tree.
-__global__ void __launch_bounds__(384)
-icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials, int nblocks,
-                 double* __restrict__ rms_log, unsigned long long* __restrict__ npairs_log,
-                 unsigned* __restrict__ stage2_log, unsigned* __restrict__ stage2_counter) {
-  if (st->done) return;
-  __shared__ double part[NS_MAX][8];
+// Runs in the LAST block of icp_iter_kernel to finish (all kBlock threads): fixed-order reduction of the
+// per-block moments, the 6-DoF solve and the loop bookkeeping of icp6D::match.  Deterministic: block b's
+// partial always enters the sum at the same place.
+__device__ __noinline__ void solve_step(IterState* __restrict__ st, const double* __restrict__ partials,
+                                           int nblocks, double* __restrict__ rms_log,
+                                           unsigned long long* __restrict__ npairs_log,
+                                           unsigned* __restrict__ stage2_log,
+                                           unsigned* __restrict__ stage2_counter) {
   __shared__ double mom[NS_MAX];
   const int tid = threadIdx.x;
   const int NS = moment_count(st->algo);
-  const int k = tid >> 3, sl = tid & 7;
-  if (k < NS) {
-    double v = 0.0;
-    for (int b = sl; b < nblocks; b += 8) v += partials[(size_t)b * NS_MAX + k];
-    part[k][sl] = v;
-  }
-  __syncthreads();
-  if (tid < NS)
-    mom[tid] = ((part[tid][0] + part[tid][1]) + (part[tid][2] + part[tid][3])) +
-               ((part[tid][4] + part[tid][5]) + (part[tid][6] + part[tid][7]));
+  // one pass: moment k is summed by S adjacent lanes (S = 8 or 4), each over an interleaved slice of the
+  // blocks, then folded with shuffles -- fixed shape, so the result does not depend on timing
+  const int S = NS <= 32 ? 8 : 4;
+  const int k = tid / S, sl = tid % S;
+  double v = 0.0;
+  if (k < NS)
+    for (int b = sl; b < nblocks; b += S) v += __ldcg(partials + (size_t)b * NS_MAX + k);
+  for (int m = S >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  if (k < NS && sl == 0) mom[k] = v;
   __syncthreads();
   if (tid != 0) return;
 
@@ -157,8 +114,8 @@ icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials
   const int iter = st->iter;
   st->prev_prev_ret = st->prev_ret;
   st->prev_ret = st->ret;
-  st->stage2_last = *stage2_counter;
-  *stage2_counter = 0;
+  st->stage2_last = atomicExch(stage2_counter, 0u);
+  const unsigned searches_now = atomicExch(stage2_counter + 1, 0u);
   const double np = mom[0];
   if (!(np > 3.0)) {  // "do we have enough point pairs?" -> break before any transform
     st->done = 1;
@@ -172,12 +129,13 @@ icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials
   for (int i = 0; i < 16; ++i) st->alignxf[i] = alignxf[i];
   rms_log[st->iters_run] = ret;
   npairs_log[st->iters_run] = (unsigned long long)(np + 0.5);
-  stage2_log[st->iters_run] = st->stage2_last;
+  stage2_log[2 * st->iters_run] = st->stage2_last;
+  stage2_log[2 * st->iters_run + 1] = searches_now;
   st->iters_run += 1;
   // Scan::transformMatrix (scan.cc:878-898): transMat <- alignxf*transMat, dalignxf <- alignxf*dalignxf
   double tmp[16];
   m4_mul(alignxf, st->X, tmp);
-  for (int i = 0; i < 16; ++i) st->X[i] = tmp[i];
+  for (int i = 0; i < 16; ++i) { st->Xprev[i] = st->X[i]; st->X[i] = tmp[i]; }
   m4_mul(alignxf, st->T, tmp);
   for (int i = 0; i < 16; ++i) st->T[i] = tmp[i];
   // transform3normal (globals.icc:1465-1475) multiplies by the transposed rotation block:
@@ -194,6 +152,189 @@ icp_solve_kernel(IterState* __restrict__ st, const double* __restrict__ partials
     st->ret_iter = iter;
   } else {
     st->iter = iter + 1;
+  }
+}
+
+constexpr int kQueueCap = 64;  // per-warp queue of queries waiting for a full search
+
+// dynamic shared memory of icp_iter_kernel
+template <int NS>
+struct IterSmem {
+  SearchSmem search;
+  int queue[kWarps][kQueueCap];
+  double acc[NS][kBlock];
+};
+
+struct PairCtx {   // everything needed to turn (query, neighbour) into moments
+  const GridDev* model;
+  const double4* dn;
+  const XfSmem* xf;
+};
+
+// forms the pair of data point i (current position t, neighbour at sorted position bj) and accumulates it
+template <bool NAPX, bool PLANE, class Acc>
+__device__ __forceinline__ void accumulate_pair(const PairCtx& pc, Acc acc, uint32_t i, int bj, double tx,
+                                                double ty, double tz) {
+  const XfSmem& xf = *pc.xf;
+  const double2 pa = __ldg(reinterpret_cast<const double2*>(pc.model->p64 + bj));
+  const double pz = __ldg(reinterpret_cast<const double*>(pc.model->p64 + bj) + 2);
+  double p1[3], p2[3] = {tx, ty, tz};
+  xf_apply(xf.S, pa.x, pa.y, pz, p1[0], p1[1], p1[2]);
+  double nv[3] = {0, 0, 0};
+  if (PLANE) {
+    const double2 na = __ldg(reinterpret_cast<const double2*>(pc.dn + i));
+    const double n2 = __ldg(reinterpret_cast<const double*>(pc.dn + i) + 2);
+    nv[0] = xf.Nm[0] * na.x + xf.Nm[1] * na.y + xf.Nm[2] * n2;
+    nv[1] = xf.Nm[3] * na.x + xf.Nm[4] * na.y + xf.Nm[5] * n2;
+    nv[2] = xf.Nm[6] * na.x + xf.Nm[7] * na.y + xf.Nm[8] * n2;
+    const double nl = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);  // Normalize3
+    nv[0] /= nl; nv[1] /= nl; nv[2] /= nl;
+    // s <- (n.(s-t)) n + t   (searchTree.cc:149-162)
+    const double dot = nv[0] * (p1[0] - p2[0]) + nv[1] * (p1[1] - p2[1]) + nv[2] * (p1[2] - p2[2]);
+    p1[0] = nv[0] * dot + p2[0];
+    p1[1] = nv[1] * dot + p2[1];
+    p1[2] = nv[2] * dot + p2[2];
+  }
+  if (NAPX) accumulate_napx(acc, p1, p2, nv, xf.o);
+  else accumulate_p2p(acc, p1, p2, xf.o);
+}
+
+// current position of data point i, its position one iteration ago and the margin worth asking for
+__device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __restrict__ dq, uint32_t i,
+                                            bool can_skip, float dmin, float dmax, double& tx, double& ty,
+                                            double& tz, double& sx, double& sy, double& sz, float& step,
+                                            float& delta) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
+  const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
+  xf_apply(xf.X, a.x, a.y, z0, tx, ty, tz);
+  xf_apply(xf.Sinv, tx, ty, tz, sx, sy, sz);
+  step = 0.f;
+  delta = 0.f;
+  if (can_skip) {
+    double px, py, pz, ux, uy, uz;
+    xf_apply(xf.Xprev, a.x, a.y, z0, px, py, pz);
+    xf_apply(xf.Sinv, px, py, pz, ux, uy, uz);
+    const double mv = sqrt((sx - ux) * (sx - ux) + (sy - uy) * (sy - uy) + (sz - uz) * (sz - uz));
+    step = __double2float_ru(mv * (1.0 + 1e-9) + 1e-12);
+    // the scanned cells certify a margin for free (nn_search.cuh); an extra one is worth scanning for only
+    // when it is small next to the typical runner-up gap and covers the motion still to come
+    delta = 8.0f * step <= dmax ? fmaxf(8.0f * step, dmin) : 0.f;
+  }
+}
+
+template <bool NAPX, bool PLANE, bool EXACT>
+__global__ void __launch_bounds__(kBlock, 3)
+icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __restrict__ dn,
+                uint32_t nd, IterState* __restrict__ st, double maxdist2, int rnd,
+                int* __restrict__ nn_cache, float* __restrict__ nn_budget, double* __restrict__ partials,
+                unsigned* __restrict__ stage2_counter, double* __restrict__ rms_log,
+                unsigned long long* __restrict__ npairs_log, unsigned* __restrict__ stage2_log) {
+  if (st->done) return;
+  constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  IterSmem<NS>& sm = *reinterpret_cast<IterSmem<NS>*>(dyn_smem);
+  __shared__ XfSmem xf;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 16) {
+    xf.X[tid] = st->X[tid]; xf.Xprev[tid] = st->Xprev[tid];
+    xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid];
+  }
+  if (tid < 9) xf.Nm[tid] = st->Nm[tid];
+  if (tid < 3) xf.o[tid] = st->o[tid];
+  const unsigned iter_salt = (unsigned)st->iter * 0x9E3779B9u;
+  // a query may skip its search while it has moved less than its certified budget (nn_search.cuh);
+  // needs the previous pose (iter > 0) and every point visited every iteration (no subsampling)
+  const bool can_skip = st->iters_run > 0 && rnd <= 1;
+  const float dmax = 0.1f * (float)model.h, dmin = 1e-3f * (float)model.h;
+  SmemAcc acc{&sm.acc[0][tid]};
+#pragma unroll 4
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  __syncthreads();
+
+  PairCtx pc{&model, dn, &xf};
+  unsigned stage2 = 0, searches = 0;
+  int qcount = 0;            // warp-uniform number of queued queries
+  int* queue = sm.queue[warp];
+
+  // full search of up to 32 queued queries, one per lane
+  auto drain = [&](int nb) {
+    const int base = qcount - nb;
+    const bool on = lane < nb;
+    uint32_t i = 0;
+    double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
+    float step = 0.f, delta = 0.f;
+    int seed = -1;
+    if (on) {
+      i = (uint32_t)queue[base + lane];
+      seed = nn_cache[i];
+      query_state(xf, dq, i, can_skip, dmin, dmax, tx, ty, tz, sx, sy, sz, step, delta);
+    }
+    int bj;
+    double bd2;
+    unsigned boidx;
+    float newbud;
+    nn_warp_search<EXACT>(model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2);
+    if (on) {
+      nn_cache[i] = bj;
+      nn_budget[i] = newbud;
+      if (bj >= 0) accumulate_pair<NAPX, PLANE>(pc, acc, i, bj, tx, ty, tz);
+    }
+    qcount = base;
+    __syncwarp();
+  };
+
+  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t i = tile * kBlock + tid;
+    bool active = i < nd;
+    if (rnd > 1 && active) active = (hash32(i ^ iter_salt) % (unsigned)rnd) == 0u;
+    bool search = false;
+    if (active) {
+      double tx, ty, tz, sx, sy, sz;
+      float step, delta;
+      query_state(xf, dq, i, can_skip, dmin, dmax, tx, ty, tz, sx, sy, sz, step, delta);
+      const float bud = can_skip ? nn_budget[i] - step : 0.f;
+      search = !(bud > 0.f);
+      if (!search) {
+        // the cached neighbour is still THE nearest neighbour; only its distance is re-evaluated
+        nn_budget[i] = bud;
+        const int seed = nn_cache[i];
+        if (seed >= 0) {
+          const double d2 = EXACT ? exact_d2(model, seed, sx, sy, sz)
+                                  : (double)dist32(__ldg(model.p32 + seed), (float)(sx - model.c[0]),
+                                                   (float)(sy - model.c[1]), (float)(sz - model.c[2]));
+          if (d2 < maxdist2) accumulate_pair<NAPX, PLANE>(pc, acc, i, seed, tx, ty, tz);
+        }
+      }
+    }
+    // queue the queries that need a full search; run them 32 at a time so every lane works
+    const unsigned smask = __ballot_sync(0xffffffffu, search);
+    if (smask) {
+      if (search) queue[qcount + __popc(smask & ((1u << lane) - 1u))] = (int)i;
+      qcount += __popc(smask);
+      if (lane == 0) searches += __popc(smask);
+      __syncwarp();
+      if (qcount >= 32) drain(32);
+    }
+  }
+  if (qcount > 0) drain(qcount);
+
+  block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+  if (lane == 0 && stage2) atomicAdd(stage2_counter, stage2);
+  if (lane == 0 && searches) atomicAdd(stage2_counter + 1, searches);
+  // ---- the last block to get here reduces all partials and runs the solve (no second launch)
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(stage2_counter + 2, 1u);
+    is_last = ticket == gridDim.x - 1;
+    if (is_last) stage2_counter[2] = 0;   // ready for the next launch
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    solve_step(st, partials, (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter);
   }
 }
 
@@ -225,7 +366,8 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
     int bj;
     double bd2;
     unsigned boidx;
-    nn_warp_search<true>(model, sm, active, sx, sy, sz, maxdist2, -1, bj, bd2, boidx, stage2);
+    float unused_budget;
+    nn_warp_search<true>(model, sm, active, sx, sy, sz, maxdist2, -1, 0.f, bj, bd2, boidx, unused_budget, stage2);
     if (active) {
       if (idx_out) idx_out[i] = bj >= 0 ? (int32_t)boidx : -1;
       if (d2_out) d2_out[i] = bj >= 0 ? bd2 : -1.0;
@@ -249,7 +391,7 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
       }
     }
   }
-  block_reduce_store<8>(acc, partials + (size_t)blockIdx.x * 8);
+  block_reduce_store_regs<8>(acc, partials + (size_t)blockIdx.x * 8);
 }
 
 // current "xyz reduced" = X * original (Scan::transformReduced), written back in original row order

@@ -20,6 +20,12 @@
 //            its own warp: rows (dy,dz) are visited ring by ring, one row per lane, clipped to the
 //            x-extent of the current search sphere; after every 32 rows a warp-shuffle arg-min merges
 //            the lanes and the loop stops as soon as the best distance is covered by the finished rings.
+//   skip     every full search also certifies a MOTION BUDGET: it scans a ball 2*delta wider than needed and
+//            records half the gap between the winner and the nearest thing that could replace it (the
+//            runner-up, or the edge of the scanned ball).  While the query has moved less than that since
+//            the search, its neighbour provably cannot have changed (triangle inequality, strict), so the
+//            caller skips the search and only re-evaluates the exact distance to the cached neighbour.
+//            In the converged phase of ICP almost every query is skipped.
 // Precision: the inner loops run in fp32 on origin-relative coordinates and track the best and the
 // second-best distance.  If the two are separated by more than the provable fp32 error the fp32 winner
 // IS the fp64 arg-min and only its distance is re-evaluated in fp64 (reference Dist2 rounding, no FMA);
@@ -176,42 +182,43 @@ __device__ __forceinline__ void cand_seed(const GridDev& g, const Best& b, float
   if (b.j >= 0) { c.d1 = dist32(__ldg(g.p32 + b.j), qx, qy, qz); c.j1 = b.j; }
 }
 
-// Searches the part of the 3x3x3 stencil that the ball (s, b.d2) touches.  `b` enters with the seed
-// (or {maxdist2, -1}) and leaves with the exact best inside that region.
-template <bool EXACT>
-__device__ __forceinline__ void stencil_search(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz,
-                                               float fx, float fy, float fz, float qx, float qy, float qz,
-                                               double sx, double sy, double sz, float e, Best& b) {
+// fp32 scan of the part of the 3x3x3 stencil that the ball of squared radius r2 (already inflated for
+// fp32 rounding) touches.  Leaves the ranges in the thread's table (`nrows` of them) and the tracking
+// state in `c` (seeded with b's point).  rc2 = squared distance from the query to the nearest cell that
+// was NOT scanned (at most h^2: the edge of the stencil) -- everything closer than that was seen, which
+// certifies a radius that is usually much larger than the ball that was asked for.
+__device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz,
+                                            float fx, float fy, float fz, float qx, float qy, float qz,
+                                            float r2, const Best& b, Cand& c, float& rc2) {
   const int tid = threadIdx.x;
   const float h = (float)g.h;
-  const float hh = h * h;
-  const float r2 = fminf(__double2float_ru(b.d2), 3.0e38f) * 1.00001f + 1e-6f * hh;
   const float lo_y = fy * fy, hi_y = (h - fy) * (h - fy);
   const float lo_z = fz * fz, hi_z = (h - fz) * (h - fz);
   const float lo_x = fx * fx, hi_x = (h - fx) * (h - fx);
   int nrows = 0;
+  rc2 = h * h;
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     const int dy = (r % 3) - 1, dz = (r / 3) - 1;
     const int y = cy + dy, z = cz + dz;
-    const float rem = r2 - (dy < 0 ? lo_y : (dy > 0 ? hi_y : 0.f)) - (dz < 0 ? lo_z : (dz > 0 ? hi_z : 0.f));
-    const int x0 = max(cx - (lo_x <= rem ? 1 : 0), 0);
-    const int x1 = min(cx + (hi_x <= rem ? 1 : 0), g.nx - 1);
-    if (rem >= 0.f && (unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz && x0 <= x1) {
+    const float dyz2 = (dy < 0 ? lo_y : (dy > 0 ? hi_y : 0.f)) + (dz < 0 ? lo_z : (dz > 0 ? hi_z : 0.f));
+    const float rem = r2 - dyz2;
+    const bool left = lo_x <= rem, right = hi_x <= rem;
+    if (rem < 0.f) { rc2 = fminf(rc2, dyz2); continue; }          // whole row left out
+    if (!left) rc2 = fminf(rc2, dyz2 + lo_x);                      // its -x / +x ends left out
+    if (!right) rc2 = fminf(rc2, dyz2 + hi_x);
+    const int x0 = max(cx - (left ? 1 : 0), 0);
+    const int x1 = min(cx + (right ? 1 : 0), g.nx - 1);
+    if ((unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz && x0 <= x1) {
       const size_t row = ((size_t)z * g.ny + y) * g.nx;
       sm.rng[2 * nrows][tid] = __ldg(g.cell_start + row + x0);
       sm.rng[2 * nrows + 1][tid] = __ldg(g.cell_start + row + x1 + 1);
       ++nrows;
     }
   }
-  Cand c;
   cand_seed(g, b, qx, qy, qz, c);
   scan_rows(g, sm, nrows, qx, qy, qz, c);
-  if (finalize_cand<EXACT>(g, c, e, sx, sy, sz, b)) return;
-  // rare: two contenders closer than the fp32 error -> settle in fp64 (ties: lowest original row)
-  b.thr = filter_bound<true>(b.d2, e);
-  for (int k = 0; k < nrows; ++k)
-    scan_range_exact(g, sm.rng[2 * k][tid], sm.rng[2 * k + 1][tid], qx, qy, qz, sx, sy, sz, e, b);
+  return nrows;
 }
 
 // ---- stage 1b ------------------------------------------------------------------------------------
@@ -221,17 +228,15 @@ __device__ __forceinline__ float slab_dist(int d, float f, float h) {
   return d > 0 ? (float)d * h - f : (d < 0 ? f + (float)(-d - 1) * h : 0.f);
 }
 
-// Thread-level exact search of the ball (s, b.d2) when it is wider than a cell: covers the cells within
-// `kmax` (<= kBallRings) of the query's cell.  Returns false if the fp32 winner is ambiguous.
-template <bool EXACT>
-__device__ __forceinline__ bool ball_scan(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz, float fx,
-                                          float fy, float fz, float qx, float qy, float qz, double sx,
-                                          double sy, double sz, float e, int kmax, Best& b) {
+// Thread-level fp32 scan of a ball wider than a cell: covers the cells within `kmax` (<= kBallRings) of
+// the query's cell.  r2 = initial squared search radius (inflated); the ball shrinks to
+// (dist(best) + 2*delta)^2 as candidates appear.  On return r2 is the final (inflated) radius.
+__device__ __forceinline__ void ball_scan(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz, float fx,
+                                          float fy, float fz, float qx, float qy, float qz, float e,
+                                          float delta, int kmax, const Best& b, float& r2, Cand& c) {
   const int tid = threadIdx.x;
   const float h = (float)g.h, inv_h = (float)g.inv_h;
   const float hh = h * h;
-  float r2 = fminf(__double2float_ru(b.d2), 3.0e38f) * 1.00001f + 1e-6f * hh;
-  Cand c;
   cand_seed(g, b, qx, qy, qz, c);
   int tz = 0, ty = 0;
   bool exhausted = false;
@@ -273,10 +278,12 @@ __device__ __forceinline__ bool ball_scan(const GridDev& g, SearchSmem& sm, int 
     for (int k = 0; k < 8; ++k)
       if (k < n) { sm.rng[2 * k][tid] = va[k]; sm.rng[2 * k + 1][tid] = vb[k]; }
     scan_rows(g, sm, n, qx, qy, qz, c);
-    // ---- shrink the ball to the (error-inflated) fp32 distance of the current best
-    if (c.j1 >= 0) r2 = fminf(r2, (c.d1 + fp32_tol(c.d1, e)) * 1.00001f + 1e-6f * hh);
+    // ---- shrink the ball to the (error-inflated) fp32 distance of the current best, plus the margin
+    if (c.j1 >= 0) {
+      const float rr = sqrtf(c.d1 + fp32_tol(c.d1, e)) * 1.00001f + 2.0f * delta;
+      r2 = fminf(r2, rr * rr * 1.00001f + 1e-6f * hh);
+    }
   }
-  return finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
 }
 
 // ring index r of flattened row f: f == 0 -> 0, else (2r-1)^2 <= f < (2r+1)^2
@@ -393,15 +400,39 @@ __device__ __forceinline__ void ring_search_warp(const GridDev& g, int cx, int c
   }
 }
 
+// Motion budget certified by a finished fp32 scan: the query may move this far (strictly less) before
+// its nearest neighbour -- or the fact that nothing is within maxdist -- can change.
+//   rcert2  squared radius of the ball that was completely scanned (not inflated)
+__device__ __forceinline__ float motion_budget(const Best& b, const Cand& c, float e, float rcert2,
+                                               double maxdist2) {
+  if (b.j >= 0) {
+    // everything except the winner is at least D2 away: scanned points by their fp32 distance minus the
+    // fp32 error, unscanned points by the radius of the scanned ball
+    const float second = fminf(c.d2nd - fp32_tol(c.d2nd, e), rcert2);
+    const double D1 = sqrt(b.d2) * (1.0 + 1e-12);
+    const double D2 = sqrt(fmax((double)second, 0.0)) * (1.0 - 1e-7);
+    const double bud = 0.5 * (D2 - D1) - 1e-12;
+    return bud > 0.0 ? __double2float_rd(bud) : 0.f;
+  }
+  // no pair: the nearest point of all is at least `nearest` away (a scanned point just outside maxdist,
+  // or the edge of the scanned ball); pairs stay impossible while the query moves less than the slack
+  const float nearest = fminf(c.d1 - fp32_tol(c.d1, e), rcert2);
+  const double bud = (sqrt(fmax((double)nearest, 0.0)) * (1.0 - 1e-7) - sqrt(maxdist2) * (1.0 + 1e-12)) - 1e-12;
+  return bud > 0.0 ? __double2float_rd(bud) : 0.f;
+}
+
 // Warp-synchronous search: every lane of every warp calls this once per tile (it contains warp
 // collectives, no block barrier).  `active` lanes carry a query s (in the grid's frame); seed_j is the
-// sorted position of the neighbour found for this query last time (-1: none).
+// sorted position of the neighbour found for this query last time (-1: none); delta >= 0 asks for a
+// motion budget (see header).  budget_out = certified budget (0 when none could be certified).
 template <bool EXACT>
 __device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm, bool active, double sx,
                                                double sy, double sz, double maxdist2, int seed_j,
-                                               int& out_j, double& out_d2, unsigned& out_oidx,
+                                               float delta, int& out_j, double& out_d2,
+                                               unsigned& out_oidx, float& budget_out,
                                                unsigned& stage2_count) {
   const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
   Best b;
   b.d2 = maxdist2;
   b.j = -1;
@@ -410,6 +441,7 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm,
   bool need2 = false;
   float qx = 0.f, qy = 0.f, qz = 0.f, e = 0.f;
   int cx = 0, cy = 0, cz = 0;
+  budget_out = 0.f;
   if (active) {
     const double ox = fmax(fmax(g.bbox_lo[0] - sx, sx - g.bbox_hi[0]), 0.0);
     const double oy = fmax(fmax(g.bbox_lo[1] - sy, sy - g.bbox_hi[1]), 0.0);
@@ -430,20 +462,47 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm,
                                 : (double)dist32(__ldg(g.p32 + seed_j), qx, qy, qz);
         if (ds < maxdist2) { b.d2 = ds; b.j = seed_j; b.oidx = __float_as_uint(__ldg(g.p32 + seed_j).w); }
       }
+      const float hh = (float)(g.h * g.h);
       const double rg2 = g.h * g.h * (1.0 - 1e-9);
-      if (b.d2 <= rg2) {
+      const double rs = sqrt(b.d2) + 2.0 * (double)delta;     // radius to certify
+      const double rs2 = rs * rs;
+      Cand c;
+      float rcert2;
+      bool settled;
+      if (rs2 <= rg2) {
         // the ball fits inside the stencil's guaranteed radius: stage 1 alone is exact
-        stencil_search<EXACT>(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, sx, sy, sz, e, b);
+        const float r2 = fminf(__double2float_ru(rs2), 3.0e38f) * 1.00001f + 1e-6f * hh;
+        float rc2;
+        const int nrows = stencil_scan(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, r2, b, c, rc2);
+        // certified radius: the requested ball, or better the (de-inflated) reach of the scanned cells
+        rcert2 = fmaxf(__double2float_rd(rs2), rc2 * 0.99999f - 2e-6f * hh);
+        settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
+        if (!settled) {  // rare: two contenders closer than the fp32 error -> settle in fp64
+          b.thr = filter_bound<true>(b.d2, e);
+          for (int k = 0; k < nrows; ++k)
+            scan_range_exact(g, sm.rng[2 * k][tid], sm.rng[2 * k + 1][tid], qx, qy, qz, sx, sy, sz, e, b);
+        }
       } else {
-        const double kneed = ceil(sqrt(b.d2) * g.inv_h);
+        const double kneed = ceil(rs * g.inv_h);
         const int kmax = (int)fmin(kneed, (double)kBallRings);
+        float r2 = fminf(__double2float_ru(rs2), 3.0e38f) * 1.00001f + 1e-6f * hh;
         const Best seed = b;
-        const bool settled = ball_scan<EXACT>(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, sx, sy, sz, e, kmax, b);
-        const double cover = (double)kmax * g.h;
+        ball_scan(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, e, delta, kmax, b, r2, c);
+        settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
+        // certified radius: the final ball, de-inflated, but never more than the scanned rings cover
+        const float cover = (float)kmax * (float)g.h;
+        rcert2 = fminf(fmaxf(r2 - 1e-6f * hh, 0.f) * 0.99997f, cover * cover * 0.99999f);
         if (!settled) { b = seed; need2 = true; }                       // fp32-ambiguous winner
-        else if (kneed > (double)kBallRings)                            // ball wider than the scan covers
-          need2 = !(b.j >= 0 && b.d2 <= cover * cover * (1.0 - 1e-9));
+        else if (kneed > (double)kBallRings) {                          // ball wider than the scan covers
+          const double cv = (double)kmax * g.h;
+          need2 = !(b.j >= 0 && b.d2 <= cv * cv * (1.0 - 1e-9));
+        }
       }
+      if (settled && !need2) budget_out = motion_budget(b, c, e, rcert2, maxdist2);
+    } else {
+      // farther than maxdist from the model's bounding box: nothing can pair until it comes closer
+      const double slack = sqrt(dbox2) * (1.0 - 1e-9) - sqrt(maxdist2) * (1.0 + 1e-12);
+      if (slack > 0.0 && slack < 1.0e30) budget_out = __double2float_rd(slack);
     }
   }
   unsigned todo = __ballot_sync(0xffffffffu, need2);

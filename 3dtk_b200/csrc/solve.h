@@ -235,6 +235,63 @@ B2_HD bool cholesky_solve(double A[N][N], const double* B, double* x) {
   return true;
 }
 
+// Eigenvector of the LARGEST eigenvalue of a symmetric 4x4 (Horn's N matrix, icp6Dquat.cc:405-463).
+// The reference takes lambda_max from the characteristic quartic (Ferrari) and the vector from an LU solve of
+// (Q - lambda I); here: quartic coefficients by the Faddeev-LeVerrier trace recurrence, lambda_max by Newton
+// from an upper bound (monotone for a polynomial with only real roots), vector = largest column of the
+// adjugate of (Q - lambda I).  A handful of dependent divisions instead of ~40 Jacobi rotations: this runs
+// on ONE thread at the end of every ICP iteration.
+B2_HD void sym4_max_eigvec(const double Q[4][4], double v[4]) {
+  double c[5] = {1.0, 0.0, 0.0, 0.0, 0.0};   // x^4 + c1 x^3 + c2 x^2 + c3 x + c4
+  double M[4][4], T[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) M[i][j] = 0.0;
+  double fro = 0.0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) fro += Q[i][j] * Q[i][j];
+  for (int k = 1; k <= 4; ++k) {   // M_k = Q M_{k-1} + c_{k-1} I ; c_k = -tr(Q M_k)/k
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double t = Q[i][0] * M[0][j] + Q[i][1] * M[1][j] + Q[i][2] * M[2][j] + Q[i][3] * M[3][j];
+        T[i][j] = t + (i == j ? c[k - 1] : 0.0);
+      }
+    double tr = 0.0;
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 4; ++j) M[i][j] = T[i][j];
+      tr += Q[i][0] * T[0][i] + Q[i][1] * T[1][i] + Q[i][2] * T[2][i] + Q[i][3] * T[3][i];
+    }
+    c[k] = -tr / (double)k;
+  }
+  double x = sqrt(fro) * (1.0 + 1e-12) + 1e-300;   // >= spectral radius >= lambda_max
+  for (int it = 0; it < 100; ++it) {
+    const double p = (((x + c[1]) * x + c[2]) * x + c[3]) * x + c[4];
+    const double dp = ((4.0 * x + 3.0 * c[1]) * x + 2.0 * c[2]) * x + c[3];
+    if (!(dp > 0.0)) break;
+    const double xn = x - p / dp;
+    if (!(xn < x)) break;          // converged to rounding (Newton approaches from the right)
+    const bool tiny = (x - xn) <= 4e-16 * fabs(x);
+    x = xn;
+    if (tiny) break;
+  }
+  double A[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) A[i][j] = Q[i][j] - (i == j ? x : 0.0);
+  // cofactor C(r,cidx) of the symmetric A
+  auto cof = [&](int r, int cc) {
+    int ri[3], ci[3], a = 0, b = 0;
+    for (int i = 0; i < 4; ++i) { if (i != r) ri[a++] = i; if (i != cc) ci[b++] = i; }
+    const double d = det3(A[ri[0]][ci[0]], A[ri[0]][ci[1]], A[ri[0]][ci[2]], A[ri[1]][ci[0]], A[ri[1]][ci[1]],
+                          A[ri[1]][ci[2]], A[ri[2]][ci[0]], A[ri[2]][ci[1]], A[ri[2]][ci[2]]);
+    return ((r + cc) & 1) ? -d : d;
+  };
+  double dg[4];
+  int best = 0;
+  for (int i = 0; i < 4; ++i) { dg[i] = cof(i, i); if (fabs(dg[i]) > fabs(dg[best])) best = i; }
+  for (int i = 0; i < 4; ++i) v[i] = i == best ? dg[i] : cof(i, best);
+  const double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  if (!(n2 > 0.0)) { v[0] = 1.0; v[1] = v[2] = v[3] = 0.0; }   // Q == lambda I: any rotation is optimal
+}
+
 // rotation from the three small-angle sines (icp6Dapx.cc:104-121 == EulerToMatrix4 with sines given)
 B2_HD void rot_from_sines(const double* x, double* M) {
   double sx = x[0], cx = sqrt(1.0 - sx * sx);
@@ -278,18 +335,16 @@ B2_HD double solve_quat(const double* mom, const double* o, double* alignxf) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) S[i][j] = mom[MP_DM + 3 * i + j] * inv - cd[i] * cm[j];
   double trace = S[0][0] + S[1][1] + S[2][2];
-  double Q[4][4], V[4][4];
+  double Q[4][4];
   Q[0][0] = trace;
   Q[0][1] = Q[1][0] = S[1][2] - S[2][1];
   Q[0][2] = Q[2][0] = S[2][0] - S[0][2];
   Q[0][3] = Q[3][0] = S[0][1] - S[1][0];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) Q[i + 1][j + 1] = S[i][j] + S[j][i] - (i == j ? trace : 0.0);
-  jacobi_eig<4>(Q, V);
-  int best = 0;
-  for (int i = 1; i < 4; ++i)
-    if (Q[i][i] > Q[best][best]) best = i;
-  double q0 = V[0][best], q1 = V[1][best], q2 = V[2][best], q3 = V[3][best];
+  double qv[4];
+  sym4_max_eigvec(Q, qv);
+  double q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3];
   double ql = 1.0 / sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
   q0 *= ql; q1 *= ql; q2 *= ql; q3 *= ql;
   // quaternion -> rotation (icp6Dquat.cc:148-169)
@@ -436,7 +491,8 @@ B2_HD double solve_any(int algo, const double* mom, const double* o, int napx_we
 }
 
 // Per-pair accumulation, shared by the host path (b200icp_align_pairs) and the kernels.
-B2_HD void accumulate_p2p(double* acc, const double* p1, const double* p2, const double* o) {
+template <class Acc>
+B2_HD void accumulate_p2p(Acc&& acc, const double* p1, const double* p2, const double* o) {
   double a[3] = {p1[0] - o[0], p1[1] - o[1], p1[2] - o[2]};
   double b[3] = {p2[0] - o[0], p2[1] - o[1], p2[2] - o[2]};
   double e0 = p1[0] - p2[0], e1 = p1[1] - p2[1], e2 = p1[2] - p2[2];
@@ -449,7 +505,8 @@ B2_HD void accumulate_p2p(double* acc, const double* p1, const double* p2, const
   acc[MP_DD + 3] += b[1] * b[1]; acc[MP_DD + 4] += b[1] * b[2]; acc[MP_DD + 5] += b[2] * b[2];
 }
 
-B2_HD void accumulate_napx(double* acc, const double* p1, const double* p2, const double* nrm,
+template <class Acc>
+B2_HD void accumulate_napx(Acc&& acc, const double* p1, const double* p2, const double* nrm,
                            const double* o) {
   double b[3] = {p2[0] - o[0], p2[1] - o[1], p2[2] - o[2]};
   double e0 = p1[0] - p2[0], e1 = p1[1] - p2[1], e2 = p1[2] - p2[2];

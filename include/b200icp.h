@@ -157,9 +157,11 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
                   uint64_t* npairs_per_iter, b200icp_match_result* result);
 
 /* Per-iteration record of the context's last b200icp_match: device time of the correspondence kernel
- * and of the solve kernel (ms; zeros unless params.profile was set) and the number of queries that
- * needed the wide ring search.  Returns the number of iterations recorded (may exceed cap). */
-int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2);
+ * and of the solve kernel (ms; zeros unless params.profile was set), the number of queries that needed
+ * the warp-level ring search, and the number that ran a full search at all (the others were certified
+ * unchanged by their motion budget).  Returns the number of iterations recorded (may exceed cap). */
+int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2,
+                         uint32_t* searches);
 
 /* ---- normals --------------------------------------------------------------------------------
  * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):
