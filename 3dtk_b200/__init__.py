@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200icp.so")
+LIB_PATH = os.environ.get("B200ICP_LIB") or os.path.join(_HERE, "lib", "libb200icp.so")  # override: A/B builds
 
 ALGO_QUAT, ALGO_SVD, ALGO_APX, ALGO_NAPX = 1, 2, 6, 10
 CLOSEST_POINT, CLOSEST_PLANE_SIMPLE = 0, 2

@@ -222,8 +222,11 @@ __device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __r
   }
 }
 
+#ifndef B200_ITER_MINBLOCKS
+#define B200_ITER_MINBLOCKS 3
+#endif
 template <bool NAPX, bool PLANE, bool EXACT>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, B200_ITER_MINBLOCKS)
 icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __restrict__ dn,
                 uint32_t nd, IterState* __restrict__ st, double maxdist2, int rnd,
                 int* __restrict__ nn_cache, float* __restrict__ nn_budget, double* __restrict__ partials,

@@ -40,6 +40,10 @@ constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 constexpr unsigned kNoIdx = 0xFFFFFFFFu;
 constexpr int kMaxRows = 9;
+#ifndef B200_SCAN_BATCH
+#define B200_SCAN_BATCH 2
+#endif
+constexpr int kScanBatch = B200_SCAN_BATCH;   // candidate loads kept in flight per lane
 constexpr int kBallRings = 8;   // thread-level ball scan covers cells up to this Chebyshev distance
 
 struct Best {
@@ -133,26 +137,34 @@ __device__ __forceinline__ void best_merge(Best& b, double od2, int oj, unsigned
 }
 
 // ---- stage 1 -------------------------------------------------------------------------------------
-// flattened fp32 scan of the first `nrows` ranges of this thread's table
+// flattened fp32 scan of the first `nrows` ranges of this thread's table.  Candidates are taken four at
+// a time: their indices come from the (cheap) range walk, then four independent 16-byte loads are in
+// flight before the first distance is needed -- the loop is bound by load latency, not arithmetic.
 __device__ __forceinline__ void scan_rows(const GridDev& g, const SearchSmem& sm, int nrows, float qx,
                                           float qy, float qz, Cand& c) {
   const int tid = threadIdx.x;
   int r = 0;
   unsigned j = 0, end = 0;
   for (;;) {
-    if (j >= end) {
-      bool more = false;
-      while (r < nrows) {
+    int idx[kScanBatch];
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u) {
+      while (j >= end && r < nrows) {
         j = sm.rng[2 * r][tid];
         end = sm.rng[2 * r + 1][tid];
         ++r;
-        if (j < end) { more = true; break; }
       }
-      if (!more) break;
+      idx[u] = j < end ? (int)j++ : -1;
     }
-    const float d = dist32(__ldg(g.p32 + j), qx, qy, qz);
-    if ((int)j != c.j1) cand_update(c, d, (int)j);   // a point met twice must not become its own runner-up
-    ++j;
+    if (idx[0] < 0) break;
+    float4 p[kScanBatch];
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u)
+      if (idx[u] >= 0) p[u] = __ldg(g.p32 + idx[u]);
+#pragma unroll
+    for (int u = 0; u < kScanBatch; ++u)
+      if (idx[u] >= 0 && idx[u] != c.j1)   // a point met twice must not become its own runner-up
+        cand_update(c, dist32(p[u], qx, qy, qz), idx[u]);
   }
 }
 
@@ -195,8 +207,10 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, in
   const float lo_y = fy * fy, hi_y = (h - fy) * (h - fy);
   const float lo_z = fz * fz, hi_z = (h - fz) * (h - fz);
   const float lo_x = fx * fx, hi_x = (h - fx) * (h - fx);
-  int nrows = 0;
   rc2 = h * h;
+  // pass 1: which rows / x-ends the ball touches, and all their range loads issued together
+  unsigned va[9], vb[9];
+  bool use[9];
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     const int dy = (r % 3) - 1, dz = (r / 3) - 1;
@@ -204,6 +218,8 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, in
     const float dyz2 = (dy < 0 ? lo_y : (dy > 0 ? hi_y : 0.f)) + (dz < 0 ? lo_z : (dz > 0 ? hi_z : 0.f));
     const float rem = r2 - dyz2;
     const bool left = lo_x <= rem, right = hi_x <= rem;
+    use[r] = false;
+    va[r] = vb[r] = 0;
     if (rem < 0.f) { rc2 = fminf(rc2, dyz2); continue; }          // whole row left out
     if (!left) rc2 = fminf(rc2, dyz2 + lo_x);                      // its -x / +x ends left out
     if (!right) rc2 = fminf(rc2, dyz2 + hi_x);
@@ -211,11 +227,20 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, in
     const int x1 = min(cx + (right ? 1 : 0), g.nx - 1);
     if ((unsigned)y < (unsigned)g.ny && (unsigned)z < (unsigned)g.nz && x0 <= x1) {
       const size_t row = ((size_t)z * g.ny + y) * g.nx;
-      sm.rng[2 * nrows][tid] = __ldg(g.cell_start + row + x0);
-      sm.rng[2 * nrows + 1][tid] = __ldg(g.cell_start + row + x1 + 1);
-      ++nrows;
+      va[r] = __ldg(g.cell_start + row + x0);
+      vb[r] = __ldg(g.cell_start + row + x1 + 1);
+      use[r] = true;
     }
   }
+  // pass 2: compact the non-empty ranges into the thread's table
+  int nrows = 0;
+#pragma unroll
+  for (int r = 0; r < 9; ++r)
+    if (use[r] && va[r] < vb[r]) {
+      sm.rng[2 * nrows][tid] = va[r];
+      sm.rng[2 * nrows + 1][tid] = vb[r];
+      ++nrows;
+    }
   cand_seed(g, b, qx, qy, qz, c);
   scan_rows(g, sm, nrows, qx, qy, qz, c);
   return nrows;
