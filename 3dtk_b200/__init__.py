@@ -74,6 +74,7 @@ def _load():
         "b200icp_align_pairs": (i32, [i32, sz, dp, dp, dp, dp, dp, dp, C.POINTER(f64)]),
         "b200icp_match": (i32, [vp, vp, vp, C.POINTER(MatchParams), dp, dp, C.POINTER(MatchResult)]),
         "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
+        "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
         "b200icp_euler_to_matrix4": (None, [dp, dp, dp]),
@@ -298,6 +299,13 @@ class icp6D:
             prof = {"nn_ms": nn, "solve_ms": sv, "stage2": s2, "searches": se}
         return {"profile": prof, "iterations": res.iterations, "iterations_run": k, "rms": rms[:k].copy(),
                 "npairs": npairs[:k].copy(), "result": res}
+
+
+def lum_link(ctx, first, second, max_dist_match2):
+    """lum6DEuler::covarianceEuler for one graph link -> (C[6,6], CD[6], npairs)"""
+    Cm, CD, n = np.zeros(36), np.zeros(6), C.c_uint64(0)
+    _check(lib.b200icp_lum_link(ctx._h, first._h, second._h, max_dist_match2, _ptr(Cm), _ptr(CD), C.byref(n)))
+    return Cm.reshape(6, 6), CD, n.value
 
 
 def normals_knn(ctx, xyz, k, rpos):

@@ -735,4 +735,89 @@ int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, co
   return B200ICP_OK;
 }
 
+// ------------------------------------------------------------------------------------ LUM link
+namespace {
+bool gauss6(double A[6][6], double* b) {
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 6; ++r) if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
+    if (A[piv][c] == 0.0) return false;
+    if (piv != c) { for (int k = 0; k < 6; ++k) std::swap(A[c][k], A[piv][k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = A[r][c] / A[c][c];
+      for (int k = c; k < 6; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 5; r >= 0; --r) {
+    double t = b[r];
+    for (int k = r + 1; k < 6; ++k) t -= A[r][k] * b[k];
+    b[r] = t / A[r][r];
+  }
+  return true;
+}
+}  // namespace
+
+int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
+                     double max_dist_match2, double C[36], double CD[6], uint64_t* npairs) {
+  if (!ctx || !first || !second || !C || !CD) return fail(B200ICP_EINVAL, "lum_link: NULL argument");
+  if (!(max_dist_match2 >= 0.0)) return fail(B200ICP_EINVAL, "lum_link: max_dist_match2 must be >= 0");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (int i = 0; i < 36; ++i) C[i] = 0.0;
+  for (int i = 0; i < 6; ++i) CD[i] = 0.0;
+  if (npairs) *npairs = 0;
+  CU_TRY(ctx->nn_cache.ensure(second->n));
+  double* hx = ctx->h_small;   // pinned, 64 doubles
+  memcpy(hx, second->dalignxf, 16 * sizeof(double));
+  memcpy(hx + 16, first->dalignxf, 16 * sizeof(double));
+  m4_inverse(first->dalignxf, hx + 32);
+  for (int i = 0; i < 6; ++i) hx[48 + i] = 0.0;
+  CU_TRY(cudaMemcpyAsync(ctx->d_small.p, hx, 54 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const uint32_t nd = (uint32_t)second->n;
+  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  const int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)(ctx->sm_count * 2));
+  std::vector<double> hp((size_t)grid * 16);
+  lum_link_kernel<1><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
+                                              ctx->nn_cache.p, ctx->partials.p);
+  CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  double s[16] = {0};
+  for (int b = 0; b < grid; ++b)
+    for (int k = 0; k < 16; ++k) s[k] += hp[(size_t)b * 16 + k];
+  const double m = s[0];
+  if (npairs) *npairs = (uint64_t)(m + 0.5);
+  if (!(m > 2.0)) return B200ICP_OK;   // "This case should not occur": C = CD = 0 (lum6Deuler.cc:243-259)
+  const double sx = s[1], sy = s[2], sz = s[3], xpy = s[4], xpz = s[5], ypz = s[6], xy = s[7], xz = s[8], yz = s[9];
+  double MM[6][6] = {{0}}, MZ[6] = {s[10], s[11], s[12], s[13], s[14], s[15]};
+  MM[0][0] = MM[1][1] = MM[2][2] = m;
+  MM[3][3] = ypz; MM[4][4] = xpy; MM[5][5] = xpz;
+  MM[0][4] = MM[4][0] = -sy; MM[0][5] = MM[5][0] = sz;
+  MM[1][3] = MM[3][1] = -sz; MM[1][4] = MM[4][1] = sx;
+  MM[2][3] = MM[3][2] = sy;  MM[2][5] = MM[5][2] = -sx;
+  MM[3][4] = MM[4][3] = -xz; MM[3][5] = MM[5][3] = -xy; MM[4][5] = MM[5][4] = -yz;
+  double A[6][6], D[6];
+  memcpy(A, MM, sizeof A);
+  memcpy(D, MZ, sizeof D);
+  if (!gauss6(A, D)) return B200ICP_OK;
+  memcpy(hx + 48, D, sizeof D);
+  CU_TRY(cudaMemcpyAsync(ctx->d_small.p + 48, hx + 48, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+  lum_link_kernel<2><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
+                                              ctx->nn_cache.p, ctx->partials.p);
+  CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  double ss = 0.0;
+  for (int b = 0; b < grid; ++b) ss += hp[(size_t)b * 16];
+  ss = ss / (2.0 * m - 3.0);
+  if (ss < 0.0000000000001) return B200ICP_OK;   // identical clouds (lum6Deuler.cc:219-231)
+  ss = 1.0 / ss;
+  for (int i = 0; i < 6; ++i) {
+    CD[i] = MZ[i] * ss;
+    for (int k = 0; k < 6; ++k) C[6 * i + k] = MM[i][k] * ss;
+  }
+  return B200ICP_OK;
+}
+
 }  // extern "C"

@@ -397,6 +397,73 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
   block_reduce_store_regs<8>(acc, partials + (size_t)blockIdx.x * 8);
 }
 
+// ---- LUM link sums: lum6DEuler::covarianceEuler (reference src/slam6d/lum6Deuler.cc:94-260) ---------------
+// PASS 1: pairs of (model grid, data scan) -> neighbour cache + the 16 sums that make MM (6x6) and MZ (6).
+// PASS 2: the pairs are re-formed from the cache (nothing moved) and the residual sum ss is taken with the
+//         pose-difference estimate D the host solved from pass 1 -- the reference's two walks over `uk`.
+// xfs: [0..15] data dalignxf, [16..31] model dalignxf, [32..47] its inverse, [48..53] D.
+// partials: [grid][16].  Sums are taken in absolute coordinates like the reference (the linearisation of
+// the LUM error is about the origin, so these moments are not shift-invariant).
+template <int PASS>
+__global__ void __launch_bounds__(kBlock, 2)
+lum_link_kernel(GridDev model, const double4* __restrict__ dq, uint32_t nd, const double* __restrict__ xfs,
+                double maxdist2, int* __restrict__ nn_cache, double* __restrict__ partials) {
+  __shared__ SearchSmem sm;
+  __shared__ double X[16], S[16], Sinv[16], D[6];
+  const int tid = threadIdx.x;
+  if (tid < 16) { X[tid] = xfs[tid]; S[tid] = xfs[16 + tid]; Sinv[tid] = xfs[32 + tid]; }
+  if (tid < 6) D[tid] = xfs[48 + tid];
+  __syncthreads();
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  unsigned stage2 = 0;
+  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t i = tile * kBlock + tid;
+    const bool active = i < nd;
+    double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
+    if (active) {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
+      const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
+      xf_apply(X, a.x, a.y, z0, tx, ty, tz);
+      xf_apply(Sinv, tx, ty, tz, sx, sy, sz);
+    }
+    int bj = -1;
+    if (PASS == 1) {
+      double bd2;
+      unsigned boidx;
+      float unused_budget;
+      nn_warp_search<true>(model, sm, active, sx, sy, sz, maxdist2, -1, 0.f, bj, bd2, boidx, unused_budget, stage2);
+      if (active) nn_cache[i] = bj;
+    } else if (active) {
+      bj = nn_cache[i];
+    }
+    if (active && bj >= 0) {
+      const double2 pa = __ldg(reinterpret_cast<const double2*>(model.p64 + bj));
+      const double pz = __ldg(reinterpret_cast<const double*>(model.p64 + bj) + 2);
+      double ax, ay, az;
+      xf_apply(S, pa.x, pa.y, pz, ax, ay, az);           // ak = p1 (model side), bk = p2 = t (data side)
+      const double x = (ax + tx) / 2.0, y = (ay + ty) / 2.0, z = (az + tz) / 2.0;
+      const double dx = ax - tx, dy = ay - ty, dz = az - tz;
+      if (PASS == 1) {
+        acc[0] += 1.0;
+        acc[1] += x; acc[2] += y; acc[3] += z;
+        acc[4] += x * x + y * y; acc[5] += x * x + z * z; acc[6] += y * y + z * z;
+        acc[7] += x * y; acc[8] += x * z; acc[9] += y * z;
+        acc[10] += dx; acc[11] += dy; acc[12] += dz;
+        acc[13] += -z * dy + y * dz; acc[14] += -y * dx + x * dy; acc[15] += z * dx - x * dz;
+      } else {
+        const double rx = dx - (D[0] - y * D[4] + z * D[5]);
+        const double ry = dy - (D[1] - z * D[3] + x * D[4]);
+        const double rz = dz - (D[2] + y * D[3] - x * D[5]);
+        acc[0] += rx * rx + ry * ry + rz * rz;
+      }
+    }
+  }
+  block_reduce_store_regs<16>(acc, partials + (size_t)blockIdx.x * 16);
+}
+
 // current "xyz reduced" = X * original (Scan::transformReduced), written back in original row order
 __global__ void scan_export_kernel(const double4* __restrict__ p64, const double4* __restrict__ nrm,
                                    const uint32_t* __restrict__ perm, uint32_t n,

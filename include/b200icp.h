@@ -163,6 +163,16 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
 int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2,
                          uint32_t* searches);
 
+/* ---- LUM link ------------------------------------------------------------------------------------
+ * Replaces: lum6DEuler::covarianceEuler (src/slam6d/lum6Deuler.cc:94-260), the per-link work of
+ * FillGB3D (:265-304): pairs of (first = Source, second = Target) by Scan::getPtPairs, the 15 running
+ * sums, D = MM^-1 MZ, the residual pass, C = MM / s^2 (row-major 6x6) and CD = MZ / s^2.  C = CD = 0
+ * when there are fewer than 3 pairs or the clouds are identical, as in the reference.  max_dist_match2
+ * is already squared (graphSlam6D::max_dist_match2_LUM).  The sparse solve of the assembled system
+ * stays on the host (it is O(scans)). */
+int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
+                     double max_dist_match2, double C[36], double CD[6], uint64_t* npairs);
+
 /* ---- normals --------------------------------------------------------------------------------
  * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):
  * exact k nearest neighbours (the point itself included), PCA, smallest-eigenvalue eigenvector,

@@ -794,3 +794,76 @@ void orc_normals_knn(const double* xyz, long n, int k, const double* rPos, doubl
 }
 
 }  // extern "C"
+
+// ---- lum6DEuler::covarianceEuler (lum6Deuler.cc:94-260): per-link 6x6 information matrix C = MM/s^2 and
+// vector CD = MZ/s^2 from the pairs of (first = model tree, second = data).  The 6x6 inverse the
+// reference takes with newmat (MM.i(), an LU factorisation) is done here by Gaussian elimination with
+// partial pivoting.  PARITY NOTE: lum6Deuler.cc itself cannot be compiled here (its header chain needs
+// CXSparse), so this function is pinned against the harness' restatement that uses the reference's
+// own newmat for the inverse, not against covarianceEuler directly.
+static bool solve6(double A[6][6], double* b) {
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 6; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (A[piv][c] == 0.0) return false;
+    if (piv != c) { for (int k = 0; k < 6; ++k) std::swap(A[c][k], A[piv][k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < 6; ++r) {
+      double f = A[r][c] / A[c][c];
+      for (int k = c; k < 6; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 5; r >= 0; --r) {
+    double t = b[r];
+    for (int k = r + 1; k < 6; ++k) t -= A[r][k] * b[k];
+    b[r] = t / A[r][r];
+  }
+  return true;
+}
+
+extern "C" long orc_lum_link(void* model_tree, const double* model_dalignxf, const double* data_xyz, long nd,
+                             double maxdist2, double* C, double* CD) {
+  std::vector<double> p1(3 * nd), p2(3 * nd);
+  double dummy_sum = 0, cm[3] = {0, 0, 0}, cd[3] = {0, 0, 0};
+  long m = orc_get_pt_pairs(model_tree, model_dalignxf, data_xyz, nullptr, 0, nd, maxdist2, 0, p1.data(),
+                            p2.data(), nullptr, nullptr, &dummy_sum, cm, cd);
+  for (int i = 0; i < 36; ++i) C[i] = 0.0;
+  for (int i = 0; i < 6; ++i) CD[i] = 0.0;
+  if (m <= 2) return m;
+  double sx = 0, sy = 0, sz = 0, xy = 0, yz = 0, xz = 0, ypz = 0, xpz = 0, xpy = 0, MZ[6] = {0, 0, 0, 0, 0, 0};
+  for (long j = 0; j < m; ++j) {
+    const double* a = &p1[3 * j];
+    const double* b = &p2[3 * j];
+    double x = (a[0] + b[0]) / 2.0, y = (a[1] + b[1]) / 2.0, z = (a[2] + b[2]) / 2.0;
+    double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    sx += x; sy += y; sz += z;
+    xpy += x * x + y * y; xpz += x * x + z * z; ypz += y * y + z * z;
+    xy += x * y; xz += x * z; yz += y * z;
+    MZ[0] += dx; MZ[1] += dy; MZ[2] += dz;
+    MZ[3] += -z * dy + y * dz; MZ[4] += -y * dx + x * dy; MZ[5] += z * dx - x * dz;
+  }
+  double MM[6][6] = {{0}};
+  MM[0][0] = MM[1][1] = MM[2][2] = (double)m;
+  MM[3][3] = ypz; MM[4][4] = xpy; MM[5][5] = xpz;
+  MM[0][4] = MM[4][0] = -sy; MM[0][5] = MM[5][0] = sz;
+  MM[1][3] = MM[3][1] = -sz; MM[1][4] = MM[4][1] = sx;
+  MM[2][3] = MM[3][2] = sy;  MM[2][5] = MM[5][2] = -sx;
+  MM[3][4] = MM[4][3] = -xz; MM[3][5] = MM[5][3] = -xy; MM[4][5] = MM[5][4] = -yz;
+  double A[6][6], D[6];
+  memcpy(A, MM, sizeof A);
+  memcpy(D, MZ, sizeof D);
+  if (!solve6(A, D)) return m;
+  double ss = 0;
+  for (long j = 0; j < m; ++j) {
+    const double* a = &p1[3 * j];
+    const double* b = &p2[3 * j];
+    double x = (a[0] + b[0]) / 2.0, y = (a[1] + b[1]) / 2.0, z = (a[2] + b[2]) / 2.0;
+    ss += sq(a[0] - b[0] - (D[0] - y * D[4] + z * D[5])) + sq(a[1] - b[1] - (D[1] - z * D[3] + x * D[4])) +
+          sq(a[2] - b[2] - (D[2] + y * D[3] - x * D[5]));
+  }
+  ss = ss / (2 * m - 3);
+  if (ss < 0.0000000000001) return m;   // identical clouds: C = CD = 0 (lum6Deuler.cc:219-231)
+  ss = 1.0 / ss;
+  for (int i = 0; i < 6; ++i) { CD[i] = MZ[i] * ss; for (int k = 0; k < 6; ++k) C[6 * i + k] = MM[i][k] * ss; }
+  return m;
+}

@@ -31,6 +31,9 @@
 #include "slam6d/icp6Dnapx.h"
 #include "slam6d/normals.h"
 #include "slam6d/globals.icc"
+#include "newmat/newmat.h"
+#include "newmat/newmatap.h"
+using namespace NEWMAT;
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -346,3 +349,58 @@ void ref_normals_knn(const double* xyz, long n, int k, const double* rPos, doubl
 }
 
 }  // extern "C"
+
+// ---- lum6DEuler::covarianceEuler (lum6Deuler.cc:94-260).  lum6Deuler.cc cannot be compiled here (its
+// header chain pulls in CXSparse), so the body is restated over the reference's getPtPairs and the
+// reference's newmat (Matrix::i()) -- a weaker pin than the functions above, and labelled as such.
+extern "C" long ref_lum_link(void* h, const double* source_alignxf, const double* data_xyz, long nd,
+                             double maxdist2, double* C_out, double* CD_out) {
+  RefTree* t = (RefTree*)h;
+  std::vector<PtPair> uk;
+  double xf[16];
+  memcpy(xf, source_alignxf, sizeof xf);
+  DataXYZ xyz_r(DataPointer((unsigned char*)data_xyz, 0));
+  DataNormal nrm_r(DataPointer((unsigned char*)0, 0));
+  double dsum = 0, dcm[3] = {0, 0, 0}, dcd[3] = {0, 0, 0};
+  {
+    CoutSilencer quiet;
+    t->tree->getPtPairs(&uk, xf, xyz_r, nrm_r, 0u, (unsigned)nd, 0, 1, maxdist2, dsum, dcm, dcd, CLOSEST_POINT);
+  }
+  int m = (int)uk.size();
+  for (int i = 0; i < 36; ++i) C_out[i] = 0.0;
+  for (int i = 0; i < 6; ++i) CD_out[i] = 0.0;
+  if (m <= 2) return m;
+  double x, y, z, sx, sy, sz, xy, yz, xz, ypz, xpz, xpy, dx, dy, dz, ss;
+  ColumnVector D(6), MZ(6);
+  Matrix MM(6, 6);
+  MZ = 0.0; MM = 0.0;
+  sx = sy = sz = xy = yz = xz = ypz = xpz = xpy = ss = 0.0;
+  for (int j = 0; j < m; j++) {
+    Point ak = uk[j].p1, bk = uk[j].p2;
+    x = (ak.x + bk.x) / 2.0; y = (ak.y + bk.y) / 2.0; z = (ak.z + bk.z) / 2.0;
+    dx = ak.x - bk.x; dy = ak.y - bk.y; dz = ak.z - bk.z;
+    sx += x; sy += y; sz += z;
+    xpy += x * x + y * y; xpz += x * x + z * z; ypz += y * y + z * z;
+    xy += x * y; xz += x * z; yz += y * z;
+    MZ(1) += dx; MZ(2) += dy; MZ(3) += dz;
+    MZ(4) += -z * dy + y * dz; MZ(5) += -y * dx + x * dy; MZ(6) += z * dx - x * dz;
+  }
+  MM(1, 1) = MM(2, 2) = MM(3, 3) = m;
+  MM(4, 4) = ypz; MM(5, 5) = xpy; MM(6, 6) = xpz;
+  MM(1, 5) = MM(5, 1) = -sy; MM(1, 6) = MM(6, 1) = sz;
+  MM(2, 4) = MM(4, 2) = -sz; MM(2, 5) = MM(5, 2) = sx;
+  MM(3, 4) = MM(4, 3) = sy;  MM(3, 6) = MM(6, 3) = -sx;
+  MM(4, 5) = MM(5, 4) = -xz; MM(4, 6) = MM(6, 4) = -xy; MM(5, 6) = MM(6, 5) = -yz;
+  D = MM.i() * MZ;
+  for (int j = 0; j < m; j++) {
+    Point ak = uk[j].p1, bk = uk[j].p2;
+    x = (ak.x + bk.x) / 2.0; y = (ak.y + bk.y) / 2.0; z = (ak.z + bk.z) / 2.0;
+    ss += sqr(ak.x - bk.x - (D(1) - y * D(5) + z * D(6))) + sqr(ak.y - bk.y - (D(2) - z * D(4) + x * D(5))) +
+          sqr(ak.z - bk.z - (D(3) + y * D(4) - x * D(6)));
+  }
+  ss = ss / (2 * m - 3);
+  if (ss < 0.0000000000001) return m;
+  ss = 1.0 / ss;
+  for (int i = 0; i < 6; ++i) { CD_out[i] = MZ(i + 1) * ss; for (int k = 0; k < 6; ++k) C_out[6 * i + k] = MM(i + 1, k + 1) * ss; }
+  return m;
+}

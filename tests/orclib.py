@@ -53,6 +53,7 @@ def port():
         L.orc_match.restype = ci
         L.orc_match.argtypes = [vp, vp, vp, vp, cl, vp, vp, ci, ci, cd, ci, cd, ci, vp, vp, vp]
         L.orc_normals_knn.restype = None; L.orc_normals_knn.argtypes = [vp, cl, ci, vp, vp]
+        L.orc_lum_link.restype = cl; L.orc_lum_link.argtypes = [vp, vp, vp, cl, cd, vp, vp]
         _port = L
     return _port
 
@@ -81,6 +82,7 @@ def ref(omp=False):
             L.ref_match.restype = ci
             L.ref_match.argtypes = [vp, vp, vp, vp, cl, vp, vp, ci, ci, cd, ci, cd, ci, ci, vp, vp, vp, vp]
             L.ref_normals_knn.restype = None; L.ref_normals_knn.argtypes = [vp, cl, ci, vp, vp]
+            L.ref_lum_link.restype = cl; L.ref_lum_link.argtypes = [vp, vp, vp, cl, cd, vp, vp]
             _ref[path] = L
     return _ref[path]
 
@@ -156,6 +158,15 @@ def ref_match(model_xyz, data_xyz, data_nrm=None, algo=1, mode=0, max_dist=25.0,
     k = done.value
     return {"iterations": it, "iterations_run": k, "transmat": T, "dalignxf": D, "rms": rms[:k],
             "npairs": npairs[:k], "xyz": d, "nrm": nrm, "ms_after_first": ms.value}
+
+
+def port_lum_link(model_xyz, data_xyz, maxdist2, model_dalignxf=None):
+    tree = PortTree(model_xyz)
+    d = np.ascontiguousarray(data_xyz, dtype=np.float64)
+    S = identity() if model_dalignxf is None else np.ascontiguousarray(model_dalignxf, dtype=np.float64)
+    Cm, CD = np.zeros(36), np.zeros(6)
+    m = port().orc_lum_link(tree.h, P(S), P(d), len(d), maxdist2, P(Cm), P(CD))
+    return Cm.reshape(6, 6), CD, m
 
 
 def rel_frobenius(a, b):

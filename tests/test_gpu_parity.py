@@ -241,3 +241,20 @@ def test_normals_knn_vs_oracle(icp, ctx, port):
     # the two smallest eigenvalues are (nearly) degenerate
     assert (dots > 1 - 1e-9).mean() > 0.999
     assert ((got * (pts - rpos)).sum(1) >= -1e-9).all()            # orientation rule normals.cc:95-104
+
+
+def test_lum_link_vs_oracle(icp, ctx):
+    """lum6DEuler::covarianceEuler on the device (two kernel passes) against the oracle."""
+    a = icp.synth_scene(7, 31, 40000, 0.5)
+    Pm = icp.euler_to_matrix4(np.array([1.5, -0.8, 0.6]), np.deg2rad([0.05, -0.08, 0.06]))
+    b = icp.transform_points(icp.m4inv(Pm)[0], icp.synth_scene(7, 32, 30000, 0.5))
+    S = icp.euler_to_matrix4(np.array([0.3, 0.1, -0.2]), np.deg2rad([0.02, 0.01, -0.03]))
+    first, second = icp.Scan(ctx, a), icp.Scan(ctx, b)
+    first.set_pose(S, S)
+    Cg, CDg, n = icp.lum_link(ctx, first, second, 100.0)
+    Cw, CDw, m = orclib.port_lum_link(a, b, 100.0, S)
+    assert n == m and m > 1000
+    np.testing.assert_allclose(Cg, Cw, rtol=1e-9)
+    np.testing.assert_allclose(CDg, CDw, rtol=1e-8, atol=1e-9 * np.abs(CDw).max())
+    Cz, CDz, nz = icp.lum_link(ctx, first, icp.Scan(ctx, a), 100.0)   # identical clouds, moved model
+    assert nz > 0

@@ -167,3 +167,25 @@ def test_live_parallel_arm_reaches_the_same_fixed_point(ref):
     ser = orclib.ref_match(model, data, algo=1, max_dist=15.0, max_iter=60, eps=1e-7)
     par = orclib.ref_match(model, data, algo=1, max_dist=15.0, max_iter=60, eps=1e-7, threads=4, omp=True)
     assert orclib.rel_frobenius(par["transmat"], ser["transmat"]) < 1e-4
+
+
+def test_live_lum_link_vs_harness_with_reference_newmat(port, ref):
+    """covarianceEuler: our Gaussian elimination vs the reference's newmat inverse (harness restatement;
+    lum6Deuler.cc itself does not compile here -- see oracle/oracle_icp.cpp)."""
+    rng = np.random.default_rng(12)
+    base = rng.uniform(-300, 300, (8000, 3)); base[:, 1] = np.abs(base[:, 1]) * 0.3
+    model = np.ascontiguousarray(base + rng.normal(0, 0.3, base.shape))
+    data = np.ascontiguousarray(base[:6000] + rng.normal(0, 0.3, (6000, 3)) + [1.0, -0.5, 0.7])
+    S = np.empty(16)
+    port.orc_euler_to_matrix4(P(np.array([0.4, 0.2, -0.3])), P(np.deg2rad([0.1, -0.2, 0.15])), P(S))
+    C1, D1, m1 = orclib.port_lum_link(model, data, 100.0, S)
+    rt = ref.ref_tree_create(P(model), len(model), 0, 20)
+    C2, D2 = np.zeros(36), np.zeros(6)
+    m2 = ref.ref_lum_link(rt, P(S), P(data), len(data), 100.0, P(C2), P(D2))
+    ref.ref_tree_free(rt)
+    assert m1 == m2 and m1 > 1000
+    np.testing.assert_allclose(C1.reshape(-1), C2, rtol=1e-9)
+    np.testing.assert_allclose(D1, D2, rtol=1e-9, atol=1e-9 * np.abs(D2).max())
+    # identical clouds -> zero information (lum6Deuler.cc:219-231)
+    C3, D3, m3 = orclib.port_lum_link(model, model, 100.0)
+    assert m3 == len(model) and not C3.any() and not D3.any()
