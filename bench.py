@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -118,6 +118,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the correspondence kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_launch_mean"]), d
+    except Exception:
+        return None, None
+
+
 def cpu_reference_run(model, data, max_iter, steps, warmup):
     """The reference's OpenMP pICP arm (icp6D.cc:129-222) from oracle/_ref on all host cores."""
     import orclib
@@ -126,7 +137,13 @@ def cpu_reference_run(model, data, max_iter, steps, warmup):
     kind = "reference"
     if L is None:
         return None
-    threads = L.ref_max_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1); the harness passes
+    # the count in an explicit num_threads clause
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except Exception:
+        threads = os.cpu_count() or 1
+    threads = max(1, min(threads, 256))
     m = np.ascontiguousarray(model)
     t0 = time.perf_counter()
     tree = L.ref_tree_create(P(m), len(m), 0, 20)
@@ -199,7 +216,18 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout; rank 0's stdout must carry exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     stream = torch.cuda.current_stream()
     ctx = icp.Context(local_rank, stream=stream.cuda_stream)
 
@@ -246,7 +274,6 @@ def main():
         launches += int(r["result"].kernel_launches)
         last = r
     barrier()
-    clocks = sampler.stop()
     wall = time.perf_counter() - wall0
     T_final, _ = d_scan.get_pose()
     pose_err = float(np.linalg.norm(T_final - Ptrue) / np.linalg.norm(Ptrue))
@@ -281,6 +308,7 @@ def main():
         e2e_t += dt
         e2e_it += r_["iterations_run"]
     barrier()
+    clocks = sampler.stop()   # sampled across both timed regions (resident steps and e2e steps)
 
     # ---- reduce over ranks: max time, summed work
     vals = torch.tensor([ms_total, float(iters_total), e2e_t, float(e2e_it), float(launches)],
@@ -305,7 +333,8 @@ def main():
     achieved = b_alg / (nn_ms * 1e-3) / 1e9 if nn_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": "icp_iter_kernel<P2P,POINT,%s>" % ("EXACT" if a.exact else "FP32"),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": ncu_traffic()[0],
+                "traffic_source": (ncu_traffic()[1] or {}).get("source"),
                 "algorithmic_bytes_per_launch": b_alg, "kernel_ms": nn_ms, "solve_kernel_ms": solve_ms,
                 "peak_source": peak_src,
                 "note": "B_alg = 16*N_d + 16*N_m + 8*N_occupied_cells + 512 (SURVEY 8d); model fits L2, the "

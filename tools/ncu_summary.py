@@ -17,6 +17,24 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_selected_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio']
+if len(sys.argv) > 2 and sys.argv[1] == '--traffic':
+    # ncu_summary.py --traffic out.json rep [rep...]: mean DRAM bytes (read+write) per launch over the reports
+    import json
+    vals, per = [], {}
+    for rep in sys.argv[3:]:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units = rows[0], rows[1]
+        for r in rows[2:]:
+            def val(name):
+                i = hdr.index(name); v = float(r[i]); u = units[i].lower()
+                return v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1)
+            b = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
+            vals.append(b); per[rep.split('/')[-1]] = {'dram_bytes': b, 'gpu_time_us': float(r[hdr.index('gpu__time_duration.sum')]) * (1e3 if units[hdr.index('gpu__time_duration.sum')] == 'ms' else 1)}
+    json.dump({'dram_bytes_per_launch_mean': sum(vals) / len(vals), 'launches': per,
+               'source': 'ncu --set full --clock-control none, icp_iter_kernel launches (cold L2: ncu flushes caches between replays)'},
+              open(sys.argv[2], 'w'), indent=1)
+    sys.exit(0)
 for rep in sys.argv[1:]:
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
