@@ -17,7 +17,9 @@
 namespace b200 {
 
 struct XfSmem {
-  double X[16], Xprev[16], Sinv[16], S[16], Nm[9], o[3];
+  double X[16], Sinv[16], S[16], Nm[9], o[3];
+  float dX[12];     // X - Xprev (rotation block + translation), fp32: per-iteration motion of a data point
+  float dXabs;      // max |entry| of the rotation block of dX (rounding bound)
 };
 
 __device__ __forceinline__ void xf_apply(const double* M, double x, double y, double z, double& ox,
@@ -90,26 +92,11 @@ __device__ __forceinline__ void block_reduce_store_regs(double (&acc)[NS], doubl
 // Runs in the LAST block of icp_iter_kernel to finish (all kBlock threads): fixed-order reduction of the
 // per-block moments, the 6-DoF solve and the loop bookkeeping of icp6D::match.  Deterministic: block b's
 // partial always enters the sum at the same place.
-__device__ __noinline__ void solve_step(IterState* __restrict__ st, const double* __restrict__ partials,
-                                           int nblocks, double* __restrict__ rms_log,
-                                           unsigned long long* __restrict__ npairs_log,
-                                           unsigned* __restrict__ stage2_log,
-                                           unsigned* __restrict__ stage2_counter) {
-  __shared__ double mom[NS_MAX];
-  const int tid = threadIdx.x;
-  const int NS = moment_count(st->algo);
-  // one pass: moment k is summed by S adjacent lanes (S = 8 or 4), each over an interleaved slice of the
-  // blocks, then folded with shuffles -- fixed shape, so the result does not depend on timing
-  const int S = NS <= 32 ? 8 : 4;
-  const int k = tid / S, sl = tid % S;
-  double v = 0.0;
-  if (k < NS)
-    for (int b = sl; b < nblocks; b += S) v += __ldcg(partials + (size_t)b * NS_MAX + k);
-  for (int m = S >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-  if (k < NS && sl == 0) mom[k] = v;
-  __syncthreads();
-  if (tid != 0) return;
-
+// The serial part of one ICP iteration (one thread; `st` lives in shared memory).
+__device__ __forceinline__ void solve_step_serial(IterState* st, const double* mom, double* __restrict__ rms_log,
+                                                  unsigned long long* __restrict__ npairs_log,
+                                                  unsigned* __restrict__ stage2_log,
+                                                  unsigned* __restrict__ stage2_counter) {
   // ---- icp6D::match loop body after getPtPairs (icp6D.cc:124-125, :229-279)
   const int iter = st->iter;
   st->prev_prev_ret = st->prev_ret;
@@ -155,6 +142,49 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ st, const double
   }
 }
 
+__device__ __noinline__ void solve_step(IterState* __restrict__ gst, const double* __restrict__ partials,
+                                        int nblocks, double* __restrict__ rms_log,
+                                        unsigned long long* __restrict__ npairs_log,
+                                        unsigned* __restrict__ stage2_log,
+                                        unsigned* __restrict__ stage2_counter, double* scratch) {
+  // scratch: >= (kWarps+1)*NS_MAX + sizeof(IterState)/8 doubles of shared memory (the accumulator columns,
+  // free by now) -- no static shared memory of its own, the kernel sits at the 3-blocks/SM limit
+  static_assert(sizeof(IterState) % 8 == 0, "IterState is copied as 8-byte words");
+  constexpr int kWords = (int)(sizeof(IterState) / 8);
+  double (*wpart)[NS_MAX] = reinterpret_cast<double (*)[NS_MAX]>(scratch);
+  double* mom = scratch + kWarps * NS_MAX;
+  double* st_raw = mom + NS_MAX;
+  IterState* st = reinterpret_cast<IterState*>(st_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // stage the loop state in shared memory: one coalesced read now, one coalesced write at the end, instead
+  // of a single thread chasing ~100 dependent global accesses
+  for (int i = tid; i < kWords; i += kBlock)
+    st_raw[i] = __ldcg(reinterpret_cast<const double*>(gst) + i);
+  const int NS = moment_count(gst->algo);
+  __syncthreads();   // scratch aliases the accumulators other warps may still be reading
+  // reduction: lane = moment, warp w takes blocks w, w+8, ... -> every load is one coalesced 184/352-byte row
+  // of a block's partials; fixed shape, so the sums do not depend on timing
+  for (int k0 = 0; k0 < NS; k0 += 32) {
+    const int k = k0 + lane;
+    double v = 0.0;
+    if (k < NS) {
+#pragma unroll 8
+      for (int b = warp; b < nblocks; b += kWarps) v += __ldcg(partials + (size_t)b * NS_MAX + k);
+      wpart[warp][k] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < NS)
+    mom[tid] = ((wpart[0][tid] + wpart[1][tid]) + (wpart[2][tid] + wpart[3][tid])) +
+               ((wpart[4][tid] + wpart[5][tid]) + (wpart[6][tid] + wpart[7][tid]));
+  __syncthreads();
+  if (tid == 0) solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
+  __syncthreads();
+  for (int i = tid; i < kWords; i += kBlock)
+    reinterpret_cast<double*>(gst)[i] = st_raw[i];
+}
+
+
 constexpr int kQueueCap = 64;  // per-warp queue of queries waiting for a full search
 
 // dynamic shared memory of icp_iter_kernel
@@ -162,6 +192,8 @@ template <int NS>
 struct IterSmem {
   SearchSmem search;
   int queue[kWarps][kQueueCap];
+  int leftover[kWarps * 32];      // end-of-kernel merge of the warps' partial queues
+  int left_count[kWarps];
   double acc[NS][kBlock];
 };
 
@@ -211,11 +243,15 @@ __device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __r
   step = 0.f;
   delta = 0.f;
   if (can_skip) {
-    double px, py, pz, ux, uy, uz;
-    xf_apply(xf.Xprev, a.x, a.y, z0, px, py, pz);
-    xf_apply(xf.Sinv, px, py, pz, ux, uy, uz);
-    const double mv = sqrt((sx - ux) * (sx - ux) + (sy - uy) * (sy - uy) + (sz - uz) * (sz - uz));
-    step = __double2float_ru(mv * (1.0 + 1e-9) + 1e-12);
+    // |s - s_prev| = |t - t_prev| (S is rigid) = |(X - Xprev) d0|, evaluated in fp32 from the fp64 difference
+    // matrix and inflated by its rounding bound: only an UPPER bound of the motion is needed
+    const float ax = (float)a.x, ay = (float)a.y, az = (float)z0;
+    const float vx = fmaf(xf.dX[0], ax, fmaf(xf.dX[3], ay, fmaf(xf.dX[6], az, xf.dX[9])));
+    const float vy = fmaf(xf.dX[1], ax, fmaf(xf.dX[4], ay, fmaf(xf.dX[7], az, xf.dX[10])));
+    const float vz = fmaf(xf.dX[2], ax, fmaf(xf.dX[5], ay, fmaf(xf.dX[8], az, xf.dX[11])));
+    const float bound = 4e-7f * (xf.dXabs * (fabsf(ax) + fabsf(ay) + fabsf(az)) + fabsf(xf.dX[9]) +
+                                 fabsf(xf.dX[10]) + fabsf(xf.dX[11]));
+    step = sqrtf(fmaf(vx, vx, fmaf(vy, vy, vz * vz))) * 1.00001f + 1.8f * bound + 1e-12f;
     // the scanned cells certify a margin for free (nn_search.cuh); an extra one is worth scanning for only
     // when it is small next to the typical runner-up gap and covers the motion still to come
     delta = 8.0f * step <= dmax ? fmaxf(8.0f * step, dmin) : 0.f;
@@ -238,12 +274,19 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   IterSmem<NS>& sm = *reinterpret_cast<IterSmem<NS>*>(dyn_smem);
   __shared__ XfSmem xf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 16) {
-    xf.X[tid] = st->X[tid]; xf.Xprev[tid] = st->Xprev[tid];
-    xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid];
-  }
+  if (tid < 16) { xf.X[tid] = st->X[tid]; xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid]; }
   if (tid < 9) xf.Nm[tid] = st->Nm[tid];
   if (tid < 3) xf.o[tid] = st->o[tid];
+  if (tid >= 32 && tid < 44) {   // dX[3c+r] = (X - Xprev)(r, c): columns 0..2 rotation block, column 3 translation
+    const int k = tid - 32, c = k / 3, r = k % 3;
+    xf.dX[k] = (float)(st->X[4 * c + r] - st->Xprev[4 * c + r]);
+  }
+  if (tid == 64) {
+    double m = 0.0;
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) m = fmax(m, fabs(st->X[4 * c + r] - st->Xprev[4 * c + r]));
+    xf.dXabs = (float)m * 1.000001f + 1e-30f;
+  }
   const unsigned iter_salt = (unsigned)st->iter * 0x9E3779B9u;
   // a query may skip its search while it has moved less than its certified budget (nn_search.cuh);
   // needs the previous pose (iter > 0) and every point visited every iteration (no subsampling)
@@ -259,16 +302,15 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   int qcount = 0;            // warp-uniform number of queued queries
   int* queue = sm.queue[warp];
 
-  // full search of up to 32 queued queries, one per lane
-  auto drain = [&](int nb) {
-    const int base = qcount - nb;
+  // full search of up to 32 queued queries (list[0..nb)), one per lane
+  auto run_batch = [&](const int* list, int nb) {
     const bool on = lane < nb;
     uint32_t i = 0;
     double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
     float step = 0.f, delta = 0.f;
     int seed = -1;
     if (on) {
-      i = (uint32_t)queue[base + lane];
+      i = (uint32_t)list[lane];
       seed = nn_cache[i];
       query_state(xf, dq, i, can_skip, dmin, dmax, tx, ty, tz, sx, sy, sz, step, delta);
     }
@@ -282,7 +324,6 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
       nn_budget[i] = newbud;
       if (bj >= 0) accumulate_pair<NAPX, PLANE>(pc, acc, i, bj, tx, ty, tz);
     }
-    qcount = base;
     __syncwarp();
   };
 
@@ -317,10 +358,25 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
       qcount += __popc(smask);
       if (lane == 0) searches += __popc(smask);
       __syncwarp();
-      if (qcount >= 32) drain(32);
+      if (qcount >= 32) { qcount -= 32; run_batch(queue + qcount, 32); }
     }
   }
-  if (qcount > 0) drain(qcount);
+  // leftovers: merge the warps' partial queues so the remaining searches run in full batches
+  if (lane == 0) sm.left_count[warp] = qcount;
+  __syncthreads();
+  {
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int n = sm.left_count[w];
+      if (w < warp) off += n;
+      total += n;
+    }
+    if (lane < qcount) sm.leftover[off + lane] = queue[lane];
+    __syncthreads();
+    for (int base = warp * 32; base < total; base += kWarps * 32)
+      run_batch(sm.leftover + base, min(32, total - base));
+  }
 
   block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
   if (lane == 0 && stage2) atomicAdd(stage2_counter, stage2);
@@ -337,7 +393,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   __syncthreads();
   if (is_last) {
     __threadfence();
-    solve_step(st, partials, (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter);
+    solve_step(st, partials, (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0]);
   }
 }
 

@@ -263,23 +263,36 @@ __device__ __forceinline__ void ball_scan(const GridDev& g, SearchSmem& sm, int 
   const float h = (float)g.h, inv_h = (float)g.inv_h;
   const float hh = h * h;
   cand_seed(g, b, qx, qy, qz, c);
-  int tz = 0, ty = 0;
+  // Row enumeration state.  Slabs are visited 0,-1,+1,-2,+2,... in z, and inside a z slab the same way in y.
+  // On either axis the slab distance grows monotonically on each side, so two consecutive misses (one per
+  // side) end that axis -- the walk costs ~(2r/h+3)^2 tests for the CURRENT radius, not (2kmax+1)^2.
+  int tz = 0, ty = 0, zmiss = 0, ymiss = 0;
+  float remz = 0.f;
+  bool zfresh = true;       // remz must be (re)computed: new slab, or the ball shrank since the last chunk
   bool exhausted = false;
   while (!exhausted) {
     // ---- gather the cell-table indices of up to 8 rows the ball touches, nearest slabs first
     int n = 0;
+    zfresh = true;
     while (n < 8) {
-      if (tz > 2 * kmax) { exhausted = true; break; }
-      const int dz = zigzag(tz);
-      const float ddz = slab_dist(dz, fz, h);
-      const float remz = r2 - ddz * ddz;
-      if (remz < 0.f || ty > 2 * kmax) { ++tz; ty = 0; continue; }
+      if (zfresh) {
+        if (tz > 2 * kmax || zmiss >= 2) { exhausted = true; break; }
+        const float ddz = slab_dist(zigzag(tz), fz, h);
+        remz = r2 - ddz * ddz;
+        zfresh = false;
+        if (remz < 0.f) { ++zmiss; ++tz; ty = 0; ymiss = 0; zfresh = true; continue; }
+        zmiss = 0;
+        if ((unsigned)(cz + zigzag(tz)) >= (unsigned)g.nz) { ++tz; ty = 0; ymiss = 0; zfresh = true; continue; }
+      }
+      if (ty > 2 * kmax || ymiss >= 2) { ++tz; ty = 0; ymiss = 0; zfresh = true; continue; }
       const int dy = zigzag(ty);
       ++ty;
       const float ddy = slab_dist(dy, fy, h);
       const float rem = remz - ddy * ddy;
-      const int y = cy + dy, z = cz + dz;
-      if (rem < 0.f || (unsigned)y >= (unsigned)g.ny || (unsigned)z >= (unsigned)g.nz) continue;
+      if (rem < 0.f) { ++ymiss; continue; }
+      ymiss = 0;
+      const int y = cy + dy, z = cz + zigzag(tz);
+      if ((unsigned)y >= (unsigned)g.ny) continue;
       const float w = sqrtf(rem) * 1.00001f + 1e-6f * h;
       const int x0 = max(cx + (int)floorf((fx - w) * inv_h), 0);
       const int x1 = min(cx + (int)floorf((fx + w) * inv_h), g.nx - 1);
