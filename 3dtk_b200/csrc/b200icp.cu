@@ -38,21 +38,40 @@ int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
   } while (0)
 
+// Device buffer.  With a stream it lives in the device's stream-ordered memory pool (cudaMallocAsync /
+// cudaFreeAsync, release threshold raised in b200icp_create): building a scan allocates ~10 buffers, and the
+// e2e path builds two scans per match -- pooled allocation keeps cudaMalloc/cudaFree (and the device-wide
+// synchronisation cudaFree implies) off that path.
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t count = 0;
+  cudaStream_t stream = nullptr;
+  bool pooled = false;
   cudaError_t alloc(size_t n) {
     release();
     count = n;
     if (n == 0) return cudaSuccess;
     return cudaMalloc((void**)&p, n * sizeof(T));
   }
+  cudaError_t alloc_async(size_t n, cudaStream_t st) {
+    release();
+    count = n;
+    if (n == 0) return cudaSuccess;
+    stream = st;
+    pooled = true;
+    return cudaMallocAsync((void**)&p, n * sizeof(T), st);
+  }
   cudaError_t ensure(size_t n) { return n <= count && p ? cudaSuccess : alloc(n); }
+  cudaError_t ensure_async(size_t n, cudaStream_t st) { return n <= count && p ? cudaSuccess : alloc_async(n, st); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pooled) cudaFreeAsync(p, stream);
+      else cudaFree(p);
+    }
     p = nullptr;
     count = 0;
+    pooled = false;
   }
   ~DevBuf() { release(); }
   DevBuf() = default;
@@ -189,6 +208,13 @@ int b200icp_create(int device, b200icp_ctx** out) {
     return fail(B200ICP_ENODEV, std::string("b200icp_create: device '") + prop.name +
                                     "' is not sm_100; kernels are built for sm_100a only");
   CU_TRY(cudaSetDevice(device));
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;   // keep freed blocks cached in the pool
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   b200icp_ctx* ctx = new b200icp_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
@@ -266,8 +292,8 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
   // ---- bbox
   const int bb_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4);
   DevBuf<double> bb_part, bb_out;
-  CU_TRY(bb_part.alloc((size_t)bb_blocks * 6));
-  CU_TRY(bb_out.alloc(6));
+  CU_TRY(bb_part.alloc_async((size_t)bb_blocks * 6, st));
+  CU_TRY(bb_out.alloc_async(6, st));
   bbox_partial_kernel<<<bb_blocks, 256, 0, st>>>(d_xyz, n, bb_part.p);
   bbox_final_kernel<<<1, 32, 0, st>>>(bb_part.p, bb_blocks, bb_out.p);
   double bb[6];
@@ -286,7 +312,7 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
   const double target_ppc = env_ppc ? std::max(atof(env_ppc), 0.25) : 3.0;
   DevBuf<uint32_t> counts;
   DevBuf<unsigned long long> occ_dev;
-  CU_TRY(occ_dev.alloc(1));
+  CU_TRY(occ_dev.alloc_async(1, st));
   GridShape gs;
   unsigned long long occ = 0;
   auto bin_points = [&](double h, uint32_t* keys, uint32_t* vals) -> cudaError_t {
@@ -294,7 +320,7 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
     gs.h = h; gs.inv_h = 1.0 / h;
     gs.nx = dims[0]; gs.ny = dims[1]; gs.nz = dims[2];
     for (int k = 0; k < 3; ++k) gs.g0[k] = bb[k];
-    cudaError_t e = counts.ensure((size_t)nc + 1);
+    cudaError_t e = counts.ensure_async((size_t)nc + 1, st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(counts.p, 0, ((size_t)nc + 1) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
@@ -333,8 +359,8 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
   DevBuf<uint32_t> keys_in, keys_out, vals_in;
   b200icp_scan* sc = new b200icp_scan();
   auto bail = [&](int code, const std::string& msg) { delete sc; return fail(code, msg); };
-  if (keys_in.alloc(n) != cudaSuccess || keys_out.alloc(n) != cudaSuccess ||
-      vals_in.alloc(n) != cudaSuccess || sc->perm.alloc(n) != cudaSuccess)
+  if (keys_in.alloc_async(n, st) != cudaSuccess || keys_out.alloc_async(n, st) != cudaSuccess ||
+      vals_in.alloc_async(n, st) != cudaSuccess || sc->perm.alloc_async(n, st) != cudaSuccess)
     return bail(B200ICP_ENOMEM, "scan_create: device allocation failed (sort buffers)");
   cudaError_t e = bin_points(h, keys_in.p, vals_in.p);
   if (e != cudaSuccess) return bail(B200ICP_ECUDA, std::string("scan_create: binning: ") + cudaGetErrorString(e));
@@ -347,16 +373,16 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts.p, counts.p, (int)(ncells + 1), st);
   DevBuf<unsigned char> tmp;
-  if (tmp.alloc(std::max(tmp_bytes, scan_bytes) + 256) != cudaSuccess ||
-      sc->cell_start.alloc(ncells + 1) != cudaSuccess || sc->p32.alloc(n) != cudaSuccess ||
-      sc->p64.alloc(n) != cudaSuccess || (d_normals && sc->nrm.alloc(n) != cudaSuccess))
+  if (tmp.alloc_async(std::max(tmp_bytes, scan_bytes) + 256, st) != cudaSuccess ||
+      sc->cell_start.alloc_async(ncells + 1, st) != cudaSuccess || sc->p32.alloc_async(n, st) != cudaSuccess ||
+      sc->p64.alloc_async(n, st) != cudaSuccess || (d_normals && sc->nrm.alloc_async(n, st) != cudaSuccess))
     return bail(B200ICP_ENOMEM, "scan_create: device allocation failed (grid buffers)");
   cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, sc->perm.p, (int)n,
                                   0, key_bits, st);
   cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, counts.p, sc->cell_start.p, (int)(ncells + 1), st);
   const unsigned gblocks = (unsigned)((n + 255) / 256);
   DevBuf<float> bmax_part;
-  if (bmax_part.alloc(gblocks) != cudaSuccess) return bail(B200ICP_ENOMEM, "scan_create: alloc");
+  if (bmax_part.alloc_async(gblocks, st) != cudaSuccess) return bail(B200ICP_ENOMEM, "scan_create: alloc");
   const double c[3] = {0.5 * (bb[0] + bb[3]), 0.5 * (bb[1] + bb[4]), 0.5 * (bb[2] + bb[5])};
   gather_kernel<<<gblocks, 256, 0, st>>>(d_xyz, d_normals, n, sc->perm.p, c[0], c[1], c[2], sc->p32.p,
                                          sc->p64.p, sc->nrm.p, bmax_part.p);
@@ -397,10 +423,10 @@ int b200icp_scan_create(b200icp_ctx* ctx, const double* xyz, const double* norma
   if (!xyz) return fail(B200ICP_EINVAL, "scan_create: xyz is NULL");
   CU_TRY(cudaSetDevice(ctx->device));
   DevBuf<double> d_xyz, d_nrm;
-  CU_TRY(d_xyz.alloc(3 * n));
+  CU_TRY(d_xyz.alloc_async(3 * n, ctx->stream));
   CU_TRY(cudaMemcpyAsync(d_xyz.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (normals) {
-    CU_TRY(d_nrm.alloc(3 * n));
+    CU_TRY(d_nrm.alloc_async(3 * n, ctx->stream));
     CU_TRY(cudaMemcpyAsync(d_nrm.p, normals, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   int rc = b200icp_scan_create_device(ctx, d_xyz.p, normals ? d_nrm.p : nullptr, n, cell_edge,
@@ -411,8 +437,8 @@ int b200icp_scan_create(b200icp_ctx* ctx, const double* xyz, const double* norma
 
 void b200icp_scan_destroy(b200icp_ctx* ctx, b200icp_scan* scan) {
   if (!scan) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  delete scan;
+  if (ctx) cudaSetDevice(ctx->device);
+  delete scan;   // buffers return to the stream-ordered pool (cudaFreeAsync on the stream that built them)
 }
 
 size_t b200icp_scan_size(const b200icp_scan* scan) { return scan ? scan->n : 0; }
