@@ -76,6 +76,7 @@ def _load():
         "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
+        "b200icp_reduce_octree_center": (i32, [vp, dp, sz, f64, dp, C.POINTER(sz)]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
         "b200icp_euler_to_matrix4": (None, [dp, dp, dp]),
         "b200icp_m4inv": (i32, [dp, dp]),
@@ -306,6 +307,15 @@ def lum_link(ctx, first, second, max_dist_match2):
     Cm, CD, n = np.zeros(36), np.zeros(6), C.c_uint64(0)
     _check(lib.b200icp_lum_link(ctx._h, first._h, second._h, max_dist_match2, _ptr(Cm), _ptr(CD), C.byref(n)))
     return Cm.reshape(6, 6), CD, n.value
+
+
+def reduce_octree_center(ctx, xyz, voxel_size):
+    """Scan::calcReducedPoints for `-r voxel_size` (octree voxel-centre reduction) -> reduced xyz"""
+    xyz = _f64(xyz, 3)
+    out = np.empty_like(xyz)
+    m = C.c_size_t(0)
+    _check(lib.b200icp_reduce_octree_center(ctx._h, _ptr(xyz), xyz.shape[0], voxel_size, _ptr(out), C.byref(m)))
+    return out[:m.value].copy()
 
 
 def normals_knn(ctx, xyz, k, rpos):

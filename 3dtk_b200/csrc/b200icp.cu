@@ -18,6 +18,7 @@
 #include "grid_build.cuh"
 #include "icp_kernels.cuh"
 #include "normals.cuh"
+#include "reduce.cuh"
 
 using namespace b200;
 
@@ -123,6 +124,10 @@ struct b200icp_scan {
   double transMat[16];
   double dalignxf[16];
   double nmat[9];                // cumulative normal map (see IterState::Nm)
+  // frees go to `st` (a live stream) instead of the stream the buffers were built on, which may be gone
+  void retarget(cudaStream_t st) {
+    cell_start.stream = st; p32.stream = st; p64.stream = st; nrm.stream = st; perm.stream = st;
+  }
 };
 
 namespace {
@@ -437,8 +442,15 @@ int b200icp_scan_create(b200icp_ctx* ctx, const double* xyz, const double* norma
 
 void b200icp_scan_destroy(b200icp_ctx* ctx, b200icp_scan* scan) {
   if (!scan) return;
-  if (ctx) cudaSetDevice(ctx->device);
-  delete scan;   // buffers return to the stream-ordered pool (cudaFreeAsync on the stream that built them)
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    scan->retarget(ctx->stream);   // buffers return to the stream-ordered pool through a stream that is alive
+  } else {
+    cudaDeviceSynchronize();       // no context left (e.g. interpreter teardown): the legacy stream is always valid
+    scan->retarget(nullptr);
+  }
+  delete scan;
 }
 
 size_t b200icp_scan_size(const b200icp_scan* scan) { return scan ? scan->n : 0; }
@@ -843,6 +855,64 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
     CD[i] = MZ[i] * ss;
     for (int k = 0; k < 6; ++k) C[6 * i + k] = MM[i][k] * ss;
   }
+  return B200ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------ octree reduction
+int b200icp_reduce_octree_center(b200icp_ctx* ctx, const double* xyz, size_t n, double voxel_size,
+                                 double* xyz_out, size_t* n_out) {
+  if (!ctx || !xyz || !xyz_out || !n_out) return fail(B200ICP_EINVAL, "reduce_octree_center: NULL argument");
+  if (!(voxel_size > 0.0)) return fail(B200ICP_EINVAL, "reduce_octree_center: voxel_size must be > 0");
+  *n_out = 0;
+  if (n == 0) return B200ICP_OK;
+  if (n >= (1ull << 31)) return fail(B200ICP_EINVAL, "reduce_octree_center: more than 2^31-1 points");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> d_xyz, bb_part, bb_out, d_out;
+  CU_TRY(d_xyz.alloc_async(3 * n, st));
+  CU_TRY(cudaMemcpyAsync(d_xyz.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int bb_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4);
+  CU_TRY(bb_part.alloc_async((size_t)bb_blocks * 6, st));
+  CU_TRY(bb_out.alloc_async(6, st));
+  bbox_partial_kernel<<<bb_blocks, 256, 0, st>>>(d_xyz.p, n, bb_part.p);
+  bbox_final_kernel<<<1, 32, 0, st>>>(bb_part.p, bb_blocks, bb_out.p);
+  double bb[6];
+  CU_TRY(cudaMemcpyAsync(bb, bb_out.p, sizeof bb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  for (int k = 0; k < 6; ++k)
+    if (!std::isfinite(bb[k])) return fail(B200ICP_EINVAL, "reduce_octree_center: non-finite coordinate");
+  OctRoot root;
+  for (int k = 0; k < 3; ++k) root.c[k] = 0.5 * (bb[k] + bb[3 + k]);             // Boctree.h:249-251
+  root.size = std::max(std::max(0.5 * (bb[3] - bb[0]), 0.5 * (bb[4] - bb[1])), 0.5 * (bb[5] - bb[2]));
+  root.size += 1.0;                                                              // Boctree.h:255
+  root.levels = 1;
+  for (double hs = root.size / 2.0; hs > voxel_size; hs /= 2.0) ++root.levels;   // leaf: child half-size <= voxel
+  if (root.levels > 21) return fail(B200ICP_EINVAL, "reduce_octree_center: voxel too small for a 63-bit octree key");
+  DevBuf<unsigned long long> k_in, k_sorted, k_uniq, d_count;
+  DevBuf<unsigned char> tmp;
+  CU_TRY(k_in.alloc_async(n, st));
+  CU_TRY(k_sorted.alloc_async(n, st));
+  CU_TRY(k_uniq.alloc_async(n, st));
+  CU_TRY(d_count.alloc_async(1, st));
+  oct_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyz.p, n, root, k_in.p);
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, b1, k_in.p, k_sorted.p, (int)n, 0, 3 * root.levels, st);
+  cub::DeviceSelect::Unique(nullptr, b2, k_sorted.p, k_uniq.p, d_count.p, (int)n, st);
+  CU_TRY(tmp.alloc_async(std::max(b1, b2) + 256, st));
+  cub::DeviceRadixSort::SortKeys(tmp.p, b1, k_in.p, k_sorted.p, (int)n, 0, 3 * root.levels, st);
+  cub::DeviceSelect::Unique(tmp.p, b2, k_sorted.p, k_uniq.p, d_count.p, (int)n, st);
+  unsigned long long m = 0;
+  CU_TRY(cudaMemcpyAsync(&m, d_count.p, sizeof m, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  // DeviceSelect::Unique writes an int-sized count for int num_items
+  m &= 0xFFFFFFFFull;
+  if (m == 0 || m > n) return fail(B200ICP_ECUDA, "reduce_octree_center: bad unique count");
+  CU_TRY(d_out.alloc_async(3 * (size_t)m, st));
+  oct_centre_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k_uniq.p, (size_t)m, root, d_out.p);
+  CU_TRY(cudaMemcpyAsync(xyz_out, d_out.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  *n_out = (size_t)m;
   return B200ICP_OK;
 }
 

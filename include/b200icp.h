@@ -180,6 +180,15 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
 int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, const double rPos[3],
                         double* normals_out);
 
+/* ---- octree reduction (the step immediately before the path) ----------------------
+ * Replaces: Scan::calcReducedPoints + BOctTree + GetOctTreeCenter for `-r voxel_size -O 0`
+ * (src/slam6d/scan.cc:560-601; include/slam6d/Boctree.h:224-270, :612-656, :928-949, :1164-1195,
+ * :1353-1355): one point per occupied leaf cube -- the cube's CENTRE -- on the reference's lattice (root cube
+ * = bbox centre, half-size = max half-extent + 1.0, halved until <= voxel_size), in its depth-first order.
+ * xyz_out must hold n rows; *n_out receives the number written.  Host pointers. */
+int b200icp_reduce_octree_center(b200icp_ctx* ctx, const double* xyz, size_t n, double voxel_size,
+                                 double* xyz_out, size_t* n_out);
+
 /* ---- synthetic inputs (host only, no GPU needed) -------------------------
  * scene(geom_seed, sample_seed, n): indoor box room 2000x300x1000 cm + 4 interior walls + 20 boxes whose
  * placement derives from geom_seed; n points sampled area-proportionally on the surfaces from

@@ -20,29 +20,7 @@ from orclib import P  # noqa: E402
 DAT = "/root/reference/dat"
 
 
-def octree_centres(pts, voxel):
-    mins, maxs = pts.min(0), pts.max(0)
-    centre = 0.5 * (mins + maxs)
-    size = float(np.max(0.5 * (maxs - mins))) + 1.0
-    out = []
-
-    def rec(idx, c, s):            # node with centre c, half-size s, points idx
-        p = pts[idx]
-        child = (p[:, 0] > c[0]).astype(np.int64) | ((p[:, 1] > c[1]).astype(np.int64) << 1) | \
-                ((p[:, 2] > c[2]).astype(np.int64) << 2)
-        for i in range(8):
-            sel = idx[child == i]
-            if len(sel) == 0:
-                continue
-            cc = c + (s / 2.0) * np.array([1 if i & 1 else -1, 1 if i & 2 else -1, 1 if i & 4 else -1], dtype=np.float64)
-            if s / 2.0 <= voxel:
-                out.append(cc)
-            else:
-                rec(sel, cc, s / 2.0)
-
-    sys.setrecursionlimit(10000)
-    rec(np.arange(len(pts)), centre, size)
-    return np.array(out)
+octree_centres = orclib.octree_centres
 
 
 def main():
@@ -59,6 +37,8 @@ def main():
         Mm = M.reshape(4, 4).T
         red = np.ascontiguousarray(red @ Mm[:3, :3].T + Mm[:3, 3])      # transformReduced(transMatOrg)
         out["scan%d_raw_count" % k] = np.array([len(pts)])
+        if k == 1:
+            out["scan1_raw_first30000"] = np.ascontiguousarray(pts[:30000])   # input of the reduction parity test
         out["scan%d_transMatOrg" % k] = M
         out["scan%d_xyz_reduced" % k] = red
         scans.append(red)

@@ -169,6 +169,38 @@ def port_lum_link(model_xyz, data_xyz, maxdist2, model_dalignxf=None):
     return Cm.reshape(6, 6), CD, m
 
 
+def octree_centres(pts, voxel):
+    """Oracle for the `-r voxel` reduction (numpy restatement of include/slam6d/Boctree.h:224-270, :612-656,
+    :928-949, :1164-1195, :1353-1355): root cube = bbox centre, half-size = max half-extent + 1.0; child index bit
+    k set iff p[k] > centre[k]; a child is a leaf when ITS half-size <= voxel; output = leaf-cube centres, depth
+    first, children 0..7.  PARITY UNPINNED against compiled reference code: Boctree.h needs Boost.Interprocess and
+    cannot be built here; the restatement follows the source line by line."""
+    import sys
+    pts = np.asarray(pts, dtype=np.float64)
+    mins, maxs = pts.min(0), pts.max(0)
+    centre = 0.5 * (mins + maxs)
+    size = float(np.max(0.5 * (maxs - mins))) + 1.0
+    out = []
+
+    def rec(idx, c, s):            # node with centre c, half-size s, points idx
+        p = pts[idx]
+        child = (p[:, 0] > c[0]).astype(np.int64) | ((p[:, 1] > c[1]).astype(np.int64) << 1) | \
+                ((p[:, 2] > c[2]).astype(np.int64) << 2)
+        for i in range(8):
+            sel = idx[child == i]
+            if len(sel) == 0:
+                continue
+            cc = c + (s / 2.0) * np.array([1 if i & 1 else -1, 1 if i & 2 else -1, 1 if i & 4 else -1], dtype=np.float64)
+            if s / 2.0 <= voxel:
+                out.append(cc)
+            else:
+                rec(sel, cc, s / 2.0)
+
+    sys.setrecursionlimit(10000)
+    rec(np.arange(len(pts)), centre, size)
+    return np.array(out)
+
+
 def rel_frobenius(a, b):
     a, b = np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))

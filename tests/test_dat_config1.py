@@ -44,3 +44,29 @@ def test_gpu_sequential_icp_on_real_scans(icp, ctx, exact):
             assert orclib.rel_frobenius(T, want) < 1e-8
         else:
             assert orclib.rel_frobenius(T, want) < 1e-4        # north-star tolerance for fp32 decisions
+
+
+def test_reduction_oracle_counts_on_raw_subset():
+    raw = GOLD["scan1_raw_first30000"]
+    red = orclib.octree_centres(raw, 10.0)
+    assert len(raw) == 30000 and 1000 < len(red) < 30000
+    # every raw point lies inside the cube (edge <= 2*voxel, Boctree.h:1168) of exactly one output centre
+    d = np.abs(raw[:, None, :] - red[None, :200, :]).max(-1)
+    assert (d.min(0) <= 10.0 + 1e-9).all()
+
+
+@pytest.mark.gpu
+def test_gpu_octree_reduction_matches_oracle(icp, ctx):
+    raw = np.ascontiguousarray(GOLD["scan1_raw_first30000"])
+    for voxel in (10.0, 3.0, 37.5):
+        got = icp.reduce_octree_center(ctx, raw, voxel)
+        want = orclib.octree_centres(raw, voxel)
+        assert got.shape == want.shape and np.array_equal(got, want)      # same centres, same depth-first order, bit-exact
+    # points exactly on splitting planes (strict '>' decides, Boctree.h:1353-1355) and a larger synthetic cloud
+    grid = np.stack(np.meshgrid(*[np.arange(-8.0, 9.0, 2.0)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    assert np.array_equal(icp.reduce_octree_center(ctx, grid, 1.0), orclib.octree_centres(grid, 1.0))
+    big = icp.synth_scene(7, 61, 200000, 0.5)
+    got, want = icp.reduce_octree_center(ctx, big, 10.0), orclib.octree_centres(big, 10.0)
+    assert np.array_equal(got, want) and len(got) < len(big)
+    one = icp.reduce_octree_center(ctx, np.array([[1.0, 2.0, 3.0]]), 10.0)
+    assert np.array_equal(one, orclib.octree_centres(np.array([[1.0, 2.0, 3.0]]), 10.0))
