@@ -258,6 +258,9 @@ __device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __r
   }
 }
 
+#ifndef B200_DUAL_TILE
+#define B200_DUAL_TILE 0
+#endif
 #ifndef B200_ITER_MINBLOCKS
 #define B200_ITER_MINBLOCKS 3
 #endif
@@ -328,9 +331,8 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   };
 
   const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t i = tile * kBlock + tid;
-    bool active = i < nd;
+  // streaming part of one query: skip path inline, otherwise report "needs a search"
+  auto stream_one = [&](uint32_t i, bool active) -> bool {
     if (rnd > 1 && active) active = (hash32(i ^ iter_salt) % (unsigned)rnd) == 0u;
     bool search = false;
     if (active) {
@@ -351,7 +353,10 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
         }
       }
     }
-    // queue the queries that need a full search; run them 32 at a time so every lane works
+    return search;
+  };
+  // queue the queries that need a full search; run them 32 at a time so every lane works
+  auto enqueue = [&](uint32_t i, bool search) {
     const unsigned smask = __ballot_sync(0xffffffffu, search);
     if (smask) {
       if (search) queue[qcount + __popc(smask & ((1u << lane) - 1u))] = (int)i;
@@ -360,7 +365,24 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
       __syncwarp();
       if (qcount >= 32) { qcount -= 32; run_batch(queue + qcount, 32); }
     }
+  };
+#if B200_DUAL_TILE
+  // two independent queries per thread and loop trip: twice the loads in flight in the latency-bound skip path
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += 2 * gridDim.x) {
+    const uint32_t i0 = tile * kBlock + tid;
+    const uint32_t tile1 = tile + gridDim.x;
+    const uint32_t i1 = tile1 * kBlock + tid;
+    const bool s0 = stream_one(i0, i0 < nd);
+    const bool s1 = stream_one(i1, tile1 < ntiles && i1 < nd);
+    enqueue(i0, s0);
+    enqueue(i1, s1);
   }
+#else
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t i = tile * kBlock + tid;
+    enqueue(i, stream_one(i, i < nd));
+  }
+#endif
   // leftovers: merge the warps' partial queues so the remaining searches run in full batches
   if (lane == 0) sm.left_count[warp] = qcount;
   __syncthreads();

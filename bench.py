@@ -43,7 +43,7 @@ POSE_THETA_DEG = (0.5, -1.0, 0.8)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
@@ -299,7 +299,7 @@ def main():
         dt = time.perf_counter() - t0
         ms_.destroy(); ds_.destroy()
         return dt, r_, pose
-    e2e_steps = max(2, min(a.steps, 5))
+    e2e_steps = max(2, min(a.steps, 10))
     e2e_step()
     barrier()
     e2e_t, e2e_it = 0.0, 0
