@@ -314,7 +314,7 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
   double h_floor = std::max(max_ext * 1e-6, 1e-9);  // smallest edge whose dense table fits the cap
   while (cells_for(ext, h_floor, dims) > (double)kCellCap) h_floor *= 1.08;
   const char* env_ppc = getenv("B200ICP_TARGET_PPC");
-  const double target_ppc = env_ppc ? std::max(atof(env_ppc), 0.25) : 3.0;
+  const double target_ppc = env_ppc ? std::max(atof(env_ppc), 0.25) : 4.0;
   DevBuf<uint32_t> counts;
   DevBuf<unsigned long long> occ_dev;
   CU_TRY(occ_dev.alloc_async(1, st));
