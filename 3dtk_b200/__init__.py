@@ -35,7 +35,7 @@ class MatchParams(C.Structure):
     _fields_ = [("algo", C.c_int), ("pairing_mode", C.c_int), ("max_dist_match", C.c_double),
                 ("max_num_iterations", C.c_int), ("epsilon_icp", C.c_double), ("rnd", C.c_int),
                 ("exact", C.c_int), ("profile", C.c_int), ("napx_weighted", C.c_int),
-                ("reserved", C.c_int * 3)]
+                ("sharded", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class MatchResult(C.Structure):
@@ -73,6 +73,11 @@ def _load():
         "b200icp_nn_batch_device": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
         "b200icp_align_pairs": (i32, [i32, sz, dp, dp, dp, dp, dp, dp, C.POINTER(f64)]),
         "b200icp_match": (i32, [vp, vp, vp, C.POINTER(MatchParams), dp, dp, C.POINTER(MatchResult)]),
+        "b200icp_comm_create": (i32, [vp, i32, i32, dp]),
+        "b200icp_comm_connect_ipc": (i32, [vp, i32, dp]),
+        "b200icp_comm_connect_local": (i32, [vp, i32, C.POINTER(vp)]),
+        "b200icp_comm_mailbox": (vp, [vp]),
+        "b200icp_comm_destroy": (i32, [vp]),
         "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
@@ -167,6 +172,23 @@ class Context:
 
     def synchronize(self):
         _check(lib.b200icp_synchronize(self._h))
+
+    # ---- query-sharded match
+    def comm_create(self, rank, world):
+        """-> 64-byte cudaIpc handle of this rank's mailbox (bytes)"""
+        buf = C.create_string_buffer(64)
+        _check(lib.b200icp_comm_create(self._h, rank, world, buf))
+        return buf.raw
+
+    def comm_connect_ipc(self, handles):
+        blob = b"".join(handles)
+        _check(lib.b200icp_comm_connect_ipc(self._h, len(handles), blob))
+
+    @staticmethod
+    def comm_connect_local(contexts):
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        for c in contexts:
+            _check(lib.b200icp_comm_connect_local(c._h, len(contexts), arr))
 
     def close(self):
         if self._h:
@@ -271,7 +293,7 @@ class icp6D:
     """Mirror of the reference's icp6D (include/slam6d/icp6D.h:27-156) for the accelerated path."""
 
     def __init__(self, ctx, algo=ALGO_QUAT, max_dist_match=25.0, max_num_iterations=50,
-                 epsilon_icp=1e-7, rnd=1, exact=True, napx_weighted=False, profile=False):
+                 epsilon_icp=1e-7, rnd=1, exact=True, napx_weighted=False, profile=False, sharded=False):
         if max_dist_match < 0.0:
             raise ValueError("ERROR [ICP6D]: first parameter (max_dist_match) has to be >= 0")
         if max_num_iterations < 0:
@@ -280,7 +302,7 @@ class icp6D:
         self.params = MatchParams(algo=algo, pairing_mode=CLOSEST_POINT, max_dist_match=max_dist_match,
                                   max_num_iterations=max_num_iterations, epsilon_icp=epsilon_icp, rnd=rnd,
                                   exact=1 if exact else 0, profile=1 if profile else 0,
-                                  napx_weighted=1 if napx_weighted else 0)
+                                  napx_weighted=1 if napx_weighted else 0, sharded=1 if sharded else 0)
 
     def match(self, previous_scan, current_scan, pairing_mode=CLOSEST_POINT):
         """-> dict(iterations, rms[], npairs[], result struct).  Updates current_scan's pose."""

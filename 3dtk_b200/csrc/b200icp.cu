@@ -107,6 +107,11 @@ struct b200icp_ctx {
   double* h_small = nullptr;        // pinned 64 doubles
   std::vector<cudaEvent_t> events;
   cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  // query-sharded match: peer mailboxes over NVLink
+  Mailbox* mailbox = nullptr;       // own, cudaMalloc'ed (IPC-exportable)
+  CommDev comm = {0, 1, 0, {nullptr}};
+  bool comm_ipc = false;
+  unsigned long long comm_matches = 0;
   int blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int blocks_per_sm_batch = 0;
 };
@@ -145,7 +150,7 @@ double cells_for(const double ext[3], double h, int dims[3]) {
 
 template <bool NAPX, bool PLANE, bool EXACT>
 cudaError_t launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const b200icp_scan* data,
-                        double maxdist2, int rnd, int* grid_out) {
+                        double maxdist2, int rnd, const CommDev& comm, int* grid_out) {
   auto kern = icp_iter_kernel<NAPX, PLANE, EXACT>;
   constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
   const size_t smem = sizeof(IterSmem<NS>);
@@ -165,22 +170,22 @@ cudaError_t launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model
   kern<<<grid, kBlock, smem, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p,
                                             maxdist2, rnd, ctx->nn_cache.p, ctx->nn_budget.p, ctx->partials.p,
                                             ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p,
-                                            ctx->stage2_log.p);
+                                            ctx->stage2_log.p, comm);
   return cudaSuccess;
 }
 
 int launch_iter_dispatch(b200icp_ctx* ctx, bool napx, bool plane, bool exact,
                          const b200icp_scan* model, const b200icp_scan* data, double maxdist2,
-                         int rnd, int* grid_out) {
+                         int rnd, const CommDev& comm, int* grid_out) {
   const int v = (napx ? 4 : 0) | (plane ? 2 : 0) | (exact ? 1 : 0);
   cudaError_t e;
   switch (v) {
-    case 0: e = launch_iter<false, false, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 1: e = launch_iter<false, false, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 2: e = launch_iter<false, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 3: e = launch_iter<false, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 6: e = launch_iter<true, true, false>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
-    case 7: e = launch_iter<true, true, true>(ctx, v, model, data, maxdist2, rnd, grid_out); break;
+    case 0: e = launch_iter<false, false, false>(ctx, v, model, data, maxdist2, rnd, comm, grid_out); break;
+    case 1: e = launch_iter<false, false, true>(ctx, v, model, data, maxdist2, rnd, comm, grid_out); break;
+    case 2: e = launch_iter<false, true, false>(ctx, v, model, data, maxdist2, rnd, comm, grid_out); break;
+    case 3: e = launch_iter<false, true, true>(ctx, v, model, data, maxdist2, rnd, comm, grid_out); break;
+    case 6: e = launch_iter<true, true, false>(ctx, v, model, data, maxdist2, rnd, comm, grid_out); break;
+    case 7: e = launch_iter<true, true, true>(ctx, v, model, data, maxdist2, rnd, comm, grid_out); break;
     default: return -1;
   }
   return e == cudaSuccess ? 0 : -2;
@@ -262,6 +267,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
   ctx->nn_cache.release();
   ctx->nn_budget.release();
   ctx->d_small.release();
+  b200icp_comm_destroy(ctx);
   if (ctx->own) cudaStreamDestroy(ctx->own);
   delete ctx;
 }
@@ -650,6 +656,13 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
 
   const double maxdist2 = prm->max_dist_match * prm->max_dist_match;
   const bool exact = prm->exact != 0;
+  CommDev comm = {0, 1, 0, {nullptr}};
+  if (prm->sharded) {
+    if (ctx->comm.world < 2) return fail(B200ICP_ESTATE, "match: params.sharded set but no communicator is connected");
+    if (prm->rnd > 1) return fail(B200ICP_EINVAL, "match: sharded match does not support rnd > 1");
+    comm = ctx->comm;
+    comm.seq_base = (++ctx->comm_matches) << 24;   // every rank calls match the same number of times
+  }
   const bool profile = prm->profile != 0;
   if (profile) {
     const size_t need = std::min<size_t>((size_t)max_iter * 3 + 3, kMaxProfileEvents);
@@ -672,7 +685,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
     for (int k = 0; k < todo; ++k) {
       const bool rec = profile && ev_i + 3 <= ctx->events.size();
       if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i], st));
-      if (launch_iter_dispatch(ctx, napx, plane, exact, model, data, maxdist2, prm->rnd, &grid) != 0)
+      if (launch_iter_dispatch(ctx, napx, plane, exact, model, data, maxdist2, prm->rnd, comm, &grid) != 0)
         return fail(B200ICP_EINVAL, "match: unsupported kernel variant");
       if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 1], st)); CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
       launches += 1;
@@ -692,6 +705,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());
   const IterState& fin = h_slots[pending];
+  if (fin.done && fin.ret_iter <= -1000)
+    return fail(B200ICP_ECUDA, "match: sharded match timed out waiting for a peer's moments");
   res.iterations = fin.done ? fin.ret_iter : max_iter;
   res.iterations_run = fin.iters_run;
   res.kernel_launches = launches;
@@ -913,6 +928,83 @@ int b200icp_reduce_octree_center(b200icp_ctx* ctx, const double* xyz, size_t n, 
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());
   *n_out = (size_t)m;
+  return B200ICP_OK;
+}
+
+// ------------------------------------------------------------------------------------ communicator
+int b200icp_comm_create(b200icp_ctx* ctx, int rank, int world, void* ipc_handle_out) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+    return fail(B200ICP_EINVAL, "comm_create: need 0 <= rank < world <= 8");
+  CU_TRY(cudaSetDevice(ctx->device));
+  b200icp_comm_destroy(ctx);
+  CU_TRY(cudaMalloc((void**)&ctx->mailbox, sizeof(Mailbox)));   // cudaMalloc (not the pool): IPC-exportable
+  CU_TRY(cudaMemset(ctx->mailbox, 0, sizeof(Mailbox)));
+  CU_TRY(cudaDeviceSynchronize());
+  ctx->comm.rank = rank;
+  ctx->comm.world = 1;            // becomes `world` once the peers are connected
+  ctx->comm.peer[rank] = ctx->mailbox;
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200ICP_COMM_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, ctx->mailbox));
+    memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  (void)world;
+  return B200ICP_OK;
+}
+
+void* b200icp_comm_mailbox(b200icp_ctx* ctx) { return ctx ? (void*)ctx->mailbox : nullptr; }
+
+int b200icp_comm_connect_ipc(b200icp_ctx* ctx, int world, const void* all_handles) {
+  if (!ctx || !ctx->mailbox || !all_handles) return fail(B200ICP_EINVAL, "comm_connect_ipc: create the communicator first");
+  if (world < 1 || world > kMaxRanks || ctx->comm.rank >= world) return fail(B200ICP_EINVAL, "comm_connect_ipc: bad world");
+  CU_TRY(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == ctx->comm.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)all_handles + (size_t)r * sizeof h, sizeof h);
+    void* p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->comm.peer[r] = (Mailbox*)p;
+  }
+  ctx->comm_ipc = true;
+  ctx->comm.world = world;
+  return B200ICP_OK;
+}
+
+int b200icp_comm_connect_local(b200icp_ctx* ctx, int world, b200icp_ctx* const* all_ctx) {
+  if (!ctx || !ctx->mailbox || !all_ctx) return fail(B200ICP_EINVAL, "comm_connect_local: create the communicator first");
+  if (world < 1 || world > kMaxRanks || ctx->comm.rank >= world) return fail(B200ICP_EINVAL, "comm_connect_local: bad world");
+  CU_TRY(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == ctx->comm.rank) continue;
+    if (!all_ctx[r] || !all_ctx[r]->mailbox) return fail(B200ICP_EINVAL, "comm_connect_local: peer has no mailbox");
+    if (all_ctx[r]->device != ctx->device) {
+      int can = 0;
+      CU_TRY(cudaDeviceCanAccessPeer(&can, ctx->device, all_ctx[r]->device));
+      if (!can) return fail(B200ICP_ENODEV, "comm_connect_local: no peer access between the devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(all_ctx[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU_TRY(e);
+      cudaGetLastError();
+    }
+    ctx->comm.peer[r] = all_ctx[r]->mailbox;
+  }
+  ctx->comm_ipc = false;
+  ctx->comm.world = world;
+  return B200ICP_OK;
+}
+
+int b200icp_comm_destroy(b200icp_ctx* ctx) {
+  if (!ctx) return B200ICP_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm_ipc)
+    for (int r = 0; r < ctx->comm.world; ++r)
+      if (r != ctx->comm.rank && ctx->comm.peer[r]) cudaIpcCloseMemHandle(ctx->comm.peer[r]);
+  if (ctx->mailbox) cudaFree(ctx->mailbox);
+  ctx->mailbox = nullptr;
+  ctx->comm = {0, 1, 0, {nullptr}};
+  ctx->comm_ipc = false;
   return B200ICP_OK;
 }
 

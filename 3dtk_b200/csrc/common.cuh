@@ -54,4 +54,19 @@ struct IterState {
   unsigned int stage2_last;
 };
 
+// Peer mailboxes of a query-sharded match.  Every rank owns one mailbox in its HBM, mapped into
+// all peers (cudaIpc across processes, peer access inside one process):
+//   box [2 slots][kMaxRanks][NS_MAX] doubles   moments of rank r for the iteration using that slot
+//   flag[2 slots][kMaxRanks]          u64      sequence number of the iteration whose moments are complete
+constexpr int kMaxRanks = 8;
+struct Mailbox {
+  double box[2][kMaxRanks][NS_MAX];
+  unsigned long long flag[2][kMaxRanks];
+};
+struct CommDev {
+  int rank, world;                 // world <= 1: single-GPU match, nothing is exchanged
+  unsigned long long seq_base;     // + loop index = sequence number of an iteration
+  Mailbox* peer[kMaxRanks];        // peer[r] = rank r's mailbox as mapped in this process (peer[rank] = own)
+};
+
 }  // namespace b200

@@ -146,7 +146,8 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
                                         int nblocks, double* __restrict__ rms_log,
                                         unsigned long long* __restrict__ npairs_log,
                                         unsigned* __restrict__ stage2_log,
-                                        unsigned* __restrict__ stage2_counter, double* scratch) {
+                                        unsigned* __restrict__ stage2_counter, double* scratch,
+                                        const CommDev& comm) {
   // scratch: >= (kWarps+1)*NS_MAX + sizeof(IterState)/8 doubles of shared memory (the accumulator columns,
   // free by now) -- no static shared memory of its own, the kernel sits at the 3-blocks/SM limit
   static_assert(sizeof(IterState) % 8 == 0, "IterState is copied as 8-byte words");
@@ -178,7 +179,46 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
     mom[tid] = ((wpart[0][tid] + wpart[1][tid]) + (wpart[2][tid] + wpart[3][tid])) +
                ((wpart[4][tid] + wpart[5][tid]) + (wpart[6][tid] + wpart[7][tid]));
   __syncthreads();
-  if (tid == 0) solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
+  if (comm.world > 1) {
+    // ---- fused all-reduce over NVLink peer memory (query-sharded match): this rank's moments are stored
+    // straight into every rank's mailbox, a flag with the iteration's sequence number follows, and every
+    // rank sums the world's rows in rank order -- bit-identical totals everywhere, so the replicated solve
+    // below keeps all ranks' loop state identical without a broadcast.
+    const unsigned long long seq = comm.seq_base + (unsigned long long)st->iter;
+    const int slot = (int)(seq & 1ull);
+    for (int p = warp; p < comm.world; p += kWarps)
+      for (int k = lane; k < NS; k += 32) comm.peer[p]->box[slot][comm.rank][k] = mom[k];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < comm.world) {
+      volatile unsigned long long* f = &comm.peer[tid]->flag[slot][comm.rank];
+      *f = seq;
+      __threadfence_system();
+    }
+    __shared__ int comm_ok;
+    if (tid == 0) comm_ok = 1;
+    __syncthreads();
+    if (tid < comm.world) {
+      volatile unsigned long long* f = &comm.peer[comm.rank]->flag[slot][tid];
+      const long long t0 = clock64();
+      while (*f != seq)
+        if (clock64() - t0 > 4000000000LL) { comm_ok = 0; break; }   // ~2 s: a peer died; do not hang the GPU
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (!comm_ok) {
+      if (tid == 0) { st->done = 1; st->ret_iter = -1000 - st->iter; }
+    } else if (tid < NS) {
+      const volatile double* row = &comm.peer[comm.rank]->box[slot][0][tid];
+      double t = 0.0;
+      for (int p = 0; p < comm.world; ++p) t += row[(size_t)p * NS_MAX];
+      mom[tid] = t;
+    }
+    __syncthreads();
+    if (tid == 0 && comm_ok) solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
+  } else if (tid == 0) {
+    solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
+  }
   __syncthreads();
   for (int i = tid; i < kWords; i += kBlock)
     reinterpret_cast<double*>(gst)[i] = st_raw[i];
@@ -270,7 +310,8 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
                 uint32_t nd, IterState* __restrict__ st, double maxdist2, int rnd,
                 int* __restrict__ nn_cache, float* __restrict__ nn_budget, double* __restrict__ partials,
                 unsigned* __restrict__ stage2_counter, double* __restrict__ rms_log,
-                unsigned long long* __restrict__ npairs_log, unsigned* __restrict__ stage2_log) {
+                unsigned long long* __restrict__ npairs_log, unsigned* __restrict__ stage2_log,
+                const __grid_constant__ CommDev comm) {
   if (st->done) return;
   constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -415,7 +456,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   __syncthreads();
   if (is_last) {
     __threadfence();
-    solve_step(st, partials, (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0]);
+    solve_step(st, partials, (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
   }
 }
 

@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-iters", type=int, default=4, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cell-edge", type=float, default=0.0)
+    ap.add_argument("--shard", default="pairs", choices=["pairs", "queries"],
+                    help="pairs: one scan pair per GPU (weak scaling, default, north_star); queries: ONE pair, data\n"
+                         "points split across GPUs, moments all-reduced inside the kernel over NVLink (strong scaling)")
     return ap.parse_args()
 
 
@@ -184,7 +187,8 @@ def main():
                           "point-to-point icp6D_QUAT, d=25 i=%d epsICP=1e-5" % (a.points, a.max_iter),
               "points_model": a.points, "points_data": a.points, "algo": "icp6D_QUAT", "max_dist": 25.0,
               "max_iter": a.max_iter, "eps_icp": 1e-5, "exact_nn": bool(a.exact),
-              "sharding": "one scan pair per GPU, no data-path collective",
+              "sharding": "one scan pair per GPU, no data-path collective" if a.shard == "pairs" else
+                          "ONE pair; data points split across GPUs; moments all-reduced in-kernel over NVLink peer memory",
               "l2": "flushed between steps (256 MiB write)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -231,16 +235,28 @@ def main():
     stream = torch.cuda.current_stream()
     ctx = icp.Context(local_rank, stream=stream.cuda_stream)
 
-    model, data, Ptrue = make_pair(icp, a.points, rank)
+    shard_q = a.shard == "queries" and world > 1
+    model, data, Ptrue = make_pair(icp, a.points, 0 if shard_q else rank)
+    n_total = a.points
+    if shard_q:
+        # whole model on every rank, contiguous slice of the data scan (scan.cc:1335-1342)
+        step_q = -(-len(data) // world)
+        data = np.ascontiguousarray(data[rank * step_q:min((rank + 1) * step_q, len(data))])
+        handle = ctx.comm_create(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        ctx.comm_connect_ipc(handles)
+        dist.barrier()
     n = a.points
+    n_data = len(data)
     # pinned host staging (e2e path)
     h_model = torch.from_numpy(model).pin_memory()
     h_data = torch.from_numpy(data).pin_memory()
     m_scan = icp.Scan.from_host_pointers(ctx, h_model.data_ptr(), None, n, a.cell_edge, 25.0)
-    d_scan = icp.Scan.from_host_pointers(ctx, h_data.data_ptr(), None, n, a.cell_edge, 25.0)
+    d_scan = icp.Scan.from_host_pointers(ctx, h_data.data_ptr(), None, n_data, a.cell_edge, 25.0)
     ginfo = m_scan.grid_info()
     eng = icp.icp6D(ctx, algo=icp.ALGO_QUAT, max_dist_match=25.0, max_num_iterations=a.max_iter,
-                    epsilon_icp=1e-5, exact=bool(a.exact))
+                    epsilon_icp=1e-5, exact=bool(a.exact), sharded=shard_q)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ident = np.eye(4).reshape(16).copy()
 
@@ -280,7 +296,7 @@ def main():
 
     # ---- kernel-level timing for the roofline (same workload, CUDA events inside the library)
     eng_prof = icp.icp6D(ctx, algo=icp.ALGO_QUAT, max_dist_match=25.0, max_num_iterations=a.max_iter,
-                         epsilon_icp=1e-5, exact=bool(a.exact), profile=True)
+                         epsilon_icp=1e-5, exact=bool(a.exact), profile=True, sharded=shard_q)
     d_scan.set_pose(ident, ident)
     flush.fill_(1)
     rp = eng_prof.match(m_scan, d_scan)
@@ -292,7 +308,7 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ms_ = icp.Scan.from_host_pointers(ctx, h_model.data_ptr(), None, n, a.cell_edge, 25.0)
-        ds_ = icp.Scan.from_host_pointers(ctx, h_data.data_ptr(), None, n, a.cell_edge, 25.0)
+        ds_ = icp.Scan.from_host_pointers(ctx, h_data.data_ptr(), None, n_data, a.cell_edge, 25.0)
         r_ = eng.match(ms_, ds_)
         pose = ds_.get_pose()[0]
         torch.cuda.synchronize()
@@ -325,8 +341,10 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    value = n * iters_sum / (ms_total * 1e-3)
-    e2e_value = n * e2e_it_sum / e2e_t
+    if shard_q:   # one pair: every rank ran the same iterations; the job's work is N_d_total x iterations
+        iters_sum, e2e_it_sum = iters_sum / world, e2e_it_sum / world
+    value = n_total * iters_sum / (ms_total * 1e-3)
+    e2e_value = n_total * e2e_it_sum / e2e_t
     hbm_peak, peak_src = peaks()
     n_occ = ginfo["n_occupied"]
     b_alg = 16.0 * n + 16.0 * n + 8.0 * n_occ + 512.0
@@ -340,12 +358,12 @@ def main():
                 "note": "B_alg = 16*N_d + 16*N_m + 8*N_occupied_cells + 512 (SURVEY 8d); model fits L2, the "
                         "kernel is L1/L2-latency and issue bound, see DESIGN.md"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong" if shard_q else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "iters_per_sec": iters_sum / (ms_total * 1e-3), "iterations_per_match": iters_total / a.steps,
             "pose_rel_frobenius_vs_truth": pose_err, "grid": ginfo, "wall_s_timed_region": wall,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 24,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (n + n_data) * 24,
                     "d2h_bytes_per_step": 2 * 640 * max(1, (a.max_iter + 3) // 4) + 16 * a.max_iter,
                     "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches, "roofline": roofline}

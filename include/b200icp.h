@@ -134,7 +134,9 @@ typedef struct b200icp_match_params {
   int exact;              /* 1: fp32 filter + fp64 verified NN (default); 0: fp32 decisions  */
   int profile;            /* 1: record per-launch CUDA-event timings (b200icp_match_profile) */
   int napx_weighted;      /* 0: B as shipped (icp6Dnapx.cc:69-74); 1: least-squares B += d*[c;n] */
-  int reserved[3];
+  int sharded;            /* 1: `data` holds only this rank's slice of the scan; moments are summed over the
+                             connected ranks inside the kernel (b200icp_comm_*); all ranks call collectively */
+  int reserved[2];
 } b200icp_match_params;
 
 typedef struct b200icp_match_result {
@@ -155,6 +157,24 @@ typedef struct b200icp_match_result {
 int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* data,
                   const b200icp_match_params* params, double* rms_per_iter,
                   uint64_t* npairs_per_iter, b200icp_match_result* result);
+
+/* ---- query-sharded match across GPUs (the reference's pICP split, scan.cc:1335-1342) --------
+ * Every rank holds the whole model scan and a contiguous slice of the data scan.  The per-iteration sum of the
+ * pair moments over all ranks is FUSED into the iteration kernel: each rank stores its moments into every
+ * rank's mailbox over NVLink (peer-mapped memory), raises a flag, sums the rows in rank order and runs the same
+ * solve -- one launch per iteration, no NCCL call, identical loop state on every rank.
+ *   b200icp_comm_create       allocates this rank's mailbox; ipc_handle_out (64 bytes, may be NULL) receives its
+ *                             cudaIpcMemHandle for other PROCESSES
+ *   b200icp_comm_connect_ipc  all_handles = world x 64 bytes in rank order (exchange them with any host
+ *                             transport, e.g. torch.distributed.all_gather)
+ *   b200icp_comm_connect_local  same-process variant: contexts on (different) devices with peer access
+ * Then call b200icp_match with params.sharded = 1 on every rank. */
+#define B200ICP_COMM_HANDLE_BYTES 64
+int b200icp_comm_create(b200icp_ctx* ctx, int rank, int world, void* ipc_handle_out);
+int b200icp_comm_connect_ipc(b200icp_ctx* ctx, int world, const void* all_handles);
+int b200icp_comm_connect_local(b200icp_ctx* ctx, int world, b200icp_ctx* const* all_ctx);
+void* b200icp_comm_mailbox(b200icp_ctx* ctx);
+int b200icp_comm_destroy(b200icp_ctx* ctx);
 
 /* Per-iteration record of the context's last b200icp_match: device time of the correspondence kernel
  * and of the solve kernel (ms; zeros unless params.profile was set), the number of queries that needed
