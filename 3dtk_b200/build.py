@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libb200icp.so")
 
 SOURCES = ["b200icp.cu", "host_util.cpp"]
-HEADERS = ["common.cuh", "grid_build.cuh", "nn_search.cuh", "icp_kernels.cuh", "normals.cuh", "reduce.cuh", "solve.h",
+HEADERS = ["common.cuh", "grid_build.cuh", "nn_search.cuh", "icp_kernels.cuh", "stream_kernels.cuh", "normals.cuh", "reduce.cuh", "solve.h",
            os.path.join("..", "..", "include", "b200icp.h")]
 
 NVCC_FLAGS = [

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "grid_build.cuh"
 #include "icp_kernels.cuh"
+#include "stream_kernels.cuh"
 #include "normals.cuh"
 #include "reduce.cuh"
 
@@ -101,6 +102,11 @@ struct b200icp_ctx {
   DevBuf<unsigned> stage2_log;
   DevBuf<int> nn_cache;             // per data point: neighbour of the previous iteration
   DevBuf<float> nn_budget;          // per data point: motion budget left before it must search again
+  DevBuf<double4> nn_pm;            // per data point: coordinates of the cached neighbour (w != 0: paired)
+  DevBuf<int> queue;                // per data point slot: search queue, one segment per stream block
+  DevBuf<unsigned> seg_count;       // [kMaxSegments] entries in each queue segment
+  int split_ready = 0;              // kernel attributes of the two-kernel iteration are set
+  int search_blocks_per_sm[4] = {0, 0, 0, 0};
   std::vector<double> prof_nn_ms, prof_solve_ms;   // last profiled match, per iteration
   std::vector<unsigned> prof_stage2;
   DevBuf<double> d_small;           // 64 doubles of scratch (transforms for API kernels)
@@ -193,6 +199,55 @@ int launch_iter_dispatch(b200icp_ctx* ctx, bool napx, bool plane, bool exact,
 
 int max_iter_grid(const b200icp_ctx* ctx) { return ctx->sm_count * kMaxBlocksPerSm; }
 
+// ---- two-kernel iteration (stream_kernels.cuh): streaming pass over every point, then the queued searches + solve
+template <bool PLANE, bool EXACT>
+cudaError_t launch_split(b200icp_ctx* ctx, int variant, const b200icp_scan* model, const b200icp_scan* data,
+                         double maxdist2, const CommDev& comm, cudaEvent_t mid) {
+  auto kstream = icp_stream_kernel<PLANE>;
+  auto ksearch = icp_search_kernel<PLANE, EXACT>;
+  const size_t smem_a = sizeof(StreamSmem), smem_b = sizeof(SearchKSmem);
+  if (ctx->search_blocks_per_sm[variant] == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kstream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ksearch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e != cudaSuccess) return e;
+    int b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ksearch, kBlock, smem_b);
+    if (e != cudaSuccess) return e;
+    ctx->search_blocks_per_sm[variant] = std::max(b, 1);
+  }
+  const uint32_t nd = (uint32_t)data->n;
+  const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  uint32_t nseg = std::min<uint32_t>(ntiles, std::min<uint32_t>((uint32_t)ctx->sm_count * 2u, (uint32_t)kMaxSegments));
+  const uint32_t tiles_per_seg = (ntiles + nseg - 1) / nseg;
+  nseg = (ntiles + tiles_per_seg - 1) / tiles_per_seg;
+  const int grid_b = (int)std::min<uint32_t>(
+      (ntiles + 0u), (uint32_t)(ctx->sm_count * std::min(ctx->search_blocks_per_sm[variant], kMaxBlocksPerSm - 2)));
+  kstream<<<nseg, kBlock, smem_a, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p, maxdist2,
+                                                 ctx->nn_pm.p, ctx->nn_budget.p, ctx->queue.p, ctx->seg_count.p,
+                                                 tiles_per_seg, ctx->partials.p);
+  if (mid) cudaEventRecord(mid, ctx->stream);
+  ksearch<<<grid_b, kBlock, smem_b, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p, maxdist2,
+                                                   ctx->nn_cache.p, ctx->nn_budget.p, ctx->nn_pm.p, ctx->queue.p,
+                                                   ctx->seg_count.p, (int)nseg, tiles_per_seg, ctx->partials.p,
+                                                   ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p,
+                                                   ctx->stage2_log.p, comm);
+  return cudaSuccess;
+}
+
+int launch_split_dispatch(b200icp_ctx* ctx, bool plane, bool exact, const b200icp_scan* model,
+                          const b200icp_scan* data, double maxdist2, const CommDev& comm, cudaEvent_t mid) {
+  const int v = (plane ? 2 : 0) | (exact ? 1 : 0);
+  cudaError_t e;
+  switch (v) {
+    case 0: e = launch_split<false, false>(ctx, v, model, data, maxdist2, comm, mid); break;
+    case 1: e = launch_split<false, true>(ctx, v, model, data, maxdist2, comm, mid); break;
+    case 2: e = launch_split<true, false>(ctx, v, model, data, maxdist2, comm, mid); break;
+    default: e = launch_split<true, true>(ctx, v, model, data, maxdist2, comm, mid); break;
+  }
+  return e == cudaSuccess ? 0 : -2;
+}
+
 }  // namespace
 
 extern "C" {
@@ -266,6 +321,9 @@ void b200icp_destroy(b200icp_ctx* ctx) {
   ctx->stage2_log.release();
   ctx->nn_cache.release();
   ctx->nn_budget.release();
+  ctx->nn_pm.release();
+  ctx->queue.release();
+  ctx->seg_count.release();
   ctx->d_small.release();
   b200icp_comm_destroy(ctx);
   if (ctx->own) cudaStreamDestroy(ctx->own);
@@ -635,6 +693,15 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   CU_TRY(ctx->stage2_log.ensure(2 * (size_t)max_iter));
   CU_TRY(ctx->nn_cache.ensure(data->n));
   CU_TRY(ctx->nn_budget.ensure(data->n));
+  // two-kernel iteration (streaming pass + queued searches) for the point-to-point moment set when every point
+  // is visited every iteration; NAPX (44 moments) and rnd > 1 keep the single fused kernel
+  static const bool force_fused = getenv("B200ICP_FUSED") != nullptr;
+  const bool split = !napx && prm->rnd <= 1 && !force_fused;
+  if (split) {
+    CU_TRY(ctx->nn_pm.ensure(data->n));
+    CU_TRY(ctx->queue.ensure(((data->n + kBlock - 1) / kBlock) * kBlock));
+    CU_TRY(ctx->seg_count.ensure(kMaxSegments));
+  }
 
   IterState* hs = ctx->h_state;
   memset(hs, 0, sizeof(IterState));
@@ -685,6 +752,14 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
     for (int k = 0; k < todo; ++k) {
       const bool rec = profile && ev_i + 3 <= ctx->events.size();
       if (rec) CU_TRY(cudaEventRecord(ctx->events[ev_i], st));
+      if (split) {
+        // events: [0] start, [1] between the stream and the search kernel, [2] end
+        if (launch_split_dispatch(ctx, plane, exact, model, data, maxdist2, comm, rec ? ctx->events[ev_i + 1] : nullptr) != 0)
+          return fail(B200ICP_ECUDA, std::string("match: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
+        launches += 2;
+        continue;
+      }
       if (launch_iter_dispatch(ctx, napx, plane, exact, model, data, maxdist2, prm->rnd, comm, &grid) != 0)
         return fail(B200ICP_EINVAL, "match: unsupported kernel variant");
       if (rec) { CU_TRY(cudaEventRecord(ctx->events[ev_i + 1], st)); CU_TRY(cudaEventRecord(ctx->events[ev_i + 2], st)); ev_i += 3; }
@@ -737,6 +812,10 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, ctx->events[3 * i], ctx->events[3 * i + 1]);
       cudaEventElapsedTime(&b, ctx->events[3 * i + 1], ctx->events[3 * i + 2]);
+      // fused kernel: a = the iteration kernel, b = nothing (the solve runs in its last block).
+      // two-kernel iteration: a = streaming kernel, b = search kernel (+ solve) -> report the search kernel as
+      // "nn" and the streaming kernel in the second slot
+      if (split) std::swap(a, b);
       ctx->prof_nn_ms.push_back(a); ctx->prof_solve_ms.push_back(b);
       nn_ms += a; sv_ms += b; ++cnt;
     }

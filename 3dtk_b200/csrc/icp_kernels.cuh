@@ -244,14 +244,13 @@ struct PairCtx {   // everything needed to turn (query, neighbour) into moments
 };
 
 // forms the pair of data point i (current position t, neighbour at sorted position bj) and accumulates it
+// (mx,my,mz) = the neighbour's coordinates in the model grid's frame (p64 of the model scan)
 template <bool NAPX, bool PLANE, class Acc>
-__device__ __forceinline__ void accumulate_pair(const PairCtx& pc, Acc acc, uint32_t i, int bj, double tx,
-                                                double ty, double tz) {
+__device__ __forceinline__ void accumulate_pair_pt(const PairCtx& pc, Acc&& acc, uint32_t i, double mx, double my,
+                                                   double mz, double tx, double ty, double tz) {
   const XfSmem& xf = *pc.xf;
-  const double2 pa = __ldg(reinterpret_cast<const double2*>(pc.model->p64 + bj));
-  const double pz = __ldg(reinterpret_cast<const double*>(pc.model->p64 + bj) + 2);
   double p1[3], p2[3] = {tx, ty, tz};
-  xf_apply(xf.S, pa.x, pa.y, pz, p1[0], p1[1], p1[2]);
+  xf_apply(xf.S, mx, my, mz, p1[0], p1[1], p1[2]);
   double nv[3] = {0, 0, 0};
   if (PLANE) {
     const double2 na = __ldg(reinterpret_cast<const double2*>(pc.dn + i));
@@ -271,13 +270,20 @@ __device__ __forceinline__ void accumulate_pair(const PairCtx& pc, Acc acc, uint
   else accumulate_p2p(acc, p1, p2, xf.o);
 }
 
+template <bool NAPX, bool PLANE, class Acc>
+__device__ __forceinline__ void accumulate_pair(const PairCtx& pc, Acc&& acc, uint32_t i, int bj, double tx,
+                                                double ty, double tz) {
+  const double2 pa = __ldg(reinterpret_cast<const double2*>(pc.model->p64 + bj));
+  const double pz = __ldg(reinterpret_cast<const double*>(pc.model->p64 + bj) + 2);
+  accumulate_pair_pt<NAPX, PLANE>(pc, acc, i, pa.x, pa.y, pz, tx, ty, tz);
+}
+
 // current position of data point i, its position one iteration ago and the margin worth asking for
-__device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __restrict__ dq, uint32_t i,
-                                            bool can_skip, float dmin, float dmax, double& tx, double& ty,
-                                            double& tz, double& sx, double& sy, double& sz, float& step,
-                                            float& delta) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
-  const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
+struct Pt3 { double x, y; };
+__device__ __forceinline__ void query_state_pt(const XfSmem& xf, const Pt3 a, const double z0,
+                                               bool can_skip, float dmin, float dmax, double& tx, double& ty,
+                                               double& tz, double& sx, double& sy, double& sz, float& step,
+                                               float& delta) {
   xf_apply(xf.X, a.x, a.y, z0, tx, ty, tz);
   xf_apply(xf.Sinv, tx, ty, tz, sx, sy, sz);
   step = 0.f;
@@ -295,6 +301,33 @@ __device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __r
     // the scanned cells certify a margin for free (nn_search.cuh); an extra one is worth scanning for only
     // when it is small next to the typical runner-up gap and covers the motion still to come
     delta = 8.0f * step <= dmax ? fmaxf(8.0f * step, dmin) : 0.f;
+  }
+}
+
+__device__ __forceinline__ void query_state(const XfSmem& xf, const double4* __restrict__ dq, uint32_t i,
+                                            bool can_skip, float dmin, float dmax, double& tx, double& ty,
+                                            double& tz, double& sx, double& sy, double& sz, float& step,
+                                            float& delta) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(dq + i));
+  const double z0 = __ldg(reinterpret_cast<const double*>(dq + i) + 2);
+  query_state_pt(xf, Pt3{a.x, a.y}, z0, can_skip, dmin, dmax, tx, ty, tz, sx, sy, sz, step, delta);
+}
+
+// stages the transforms of the running iteration in shared memory (all threads call; caller syncs)
+__device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict__ st) {
+  const int tid = threadIdx.x;
+  if (tid < 16) { xf.X[tid] = st->X[tid]; xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid]; }
+  if (tid < 9) xf.Nm[tid] = st->Nm[tid];
+  if (tid < 3) xf.o[tid] = st->o[tid];
+  if (tid >= 32 && tid < 44) {   // dX[3c+r] = (X - Xprev)(r, c): columns 0..2 rotation block, column 3 translation
+    const int k = tid - 32, c = k / 3, r = k % 3;
+    xf.dX[k] = (float)(st->X[4 * c + r] - st->Xprev[4 * c + r]);
+  }
+  if (tid == 64) {
+    double m = 0.0;
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) m = fmax(m, fabs(st->X[4 * c + r] - st->Xprev[4 * c + r]));
+    xf.dXabs = (float)m * 1.000001f + 1e-30f;
   }
 }
 
@@ -318,19 +351,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   IterSmem<NS>& sm = *reinterpret_cast<IterSmem<NS>*>(dyn_smem);
   __shared__ XfSmem xf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 16) { xf.X[tid] = st->X[tid]; xf.Sinv[tid] = st->Sinv[tid]; xf.S[tid] = st->S[tid]; }
-  if (tid < 9) xf.Nm[tid] = st->Nm[tid];
-  if (tid < 3) xf.o[tid] = st->o[tid];
-  if (tid >= 32 && tid < 44) {   // dX[3c+r] = (X - Xprev)(r, c): columns 0..2 rotation block, column 3 translation
-    const int k = tid - 32, c = k / 3, r = k % 3;
-    xf.dX[k] = (float)(st->X[4 * c + r] - st->Xprev[4 * c + r]);
-  }
-  if (tid == 64) {
-    double m = 0.0;
-    for (int c = 0; c < 3; ++c)
-      for (int r = 0; r < 3; ++r) m = fmax(m, fabs(st->X[4 * c + r] - st->Xprev[4 * c + r]));
-    xf.dXabs = (float)m * 1.000001f + 1e-30f;
-  }
+  load_xf(xf, st);
   const unsigned iter_salt = (unsigned)st->iter * 0x9E3779B9u;
   // a query may skip its search while it has moved less than its certified budget (nn_search.cuh);
   // needs the previous pose (iter > 0) and every point visited every iteration (no subsampling)

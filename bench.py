@@ -67,19 +67,60 @@ def make_pair(icp, n, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    Sampled in-process through NVML (pynvml) from a thread, every 20 ms: an `nvidia-smi -lms 50` child polling
+    its full query set was measured to DOUBLE the wall-clock time of the end-to-end steps (20.1 ms vs 10.1 ms per
+    step) by contending for the driver, so nvidia-smi is only the fallback (at a 500 ms period)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index, uuid=None):
+        self.rows, self.proc, self.idx, self.uuid = [], None, gpu_index, uuid
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), None
+        self._stop = threading.Event()
+        self.th = None
+
+    def _nvml_loop(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for nm, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.how = "nvml"
+            self.th = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.how = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -90,8 +131,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.how == "nvml":
+            self._stop.set()
+            self.th.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml, 20 ms period, sampled during the timed regions"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -108,7 +155,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 500"}
 
 
 def peaks():
@@ -277,9 +324,14 @@ def main():
 
     for _ in range(a.warmup):
         resident_step()
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     barrier()
-    sampler.start()
+    if not os.environ.get("B200_BENCH_NO_SAMPLER"):
+        sampler.start()
     ms_total, iters_total, launches = 0.0, 0, 0
     wall0 = time.perf_counter()
     last = None
