@@ -223,16 +223,31 @@ cudaError_t launch_split(b200icp_ctx* ctx, int variant, const b200icp_scan* mode
   nseg = (ntiles + tiles_per_seg - 1) / tiles_per_seg;
   const int grid_b = (int)std::min<uint32_t>(
       (ntiles + 0u), (uint32_t)(ctx->sm_count * std::min(ctx->search_blocks_per_sm[variant], kMaxBlocksPerSm - 2)));
-  kstream<<<nseg, kBlock, smem_a, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p, maxdist2,
-                                                 ctx->nn_pm.p, ctx->nn_budget.p, ctx->queue.p, ctx->seg_count.p,
-                                                 tiles_per_seg, ctx->partials.p);
+  // both kernels are launched with programmatic stream serialization (PDL): launch latency and prologue of each
+  // overlap the tail of its predecessor; the kernels order themselves with griddepcontrol.wait
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kBlock);
+  cfg.stream = ctx->stream;
+  static const bool no_pdl = getenv("B200ICP_NO_PDL") != nullptr;   // A/B switch
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  cfg.gridDim = dim3(nseg);
+  cfg.dynamicSmemBytes = smem_a;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kstream, model->g, (const double4*)data->g.p64, (const double4*)data->g.nrm, nd,
+                                     (const IterState*)ctx->d_state.p, maxdist2, (const double4*)ctx->nn_pm.p,
+                                     ctx->nn_budget.p, ctx->queue.p, ctx->seg_count.p, tiles_per_seg, ctx->partials.p);
+  if (e != cudaSuccess) return e;
   if (mid) cudaEventRecord(mid, ctx->stream);
-  ksearch<<<grid_b, kBlock, smem_b, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p, maxdist2,
-                                                   ctx->nn_cache.p, ctx->nn_budget.p, ctx->nn_pm.p, ctx->queue.p,
-                                                   ctx->seg_count.p, (int)nseg, tiles_per_seg, ctx->partials.p,
-                                                   ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p,
-                                                   ctx->stage2_log.p, comm);
-  return cudaSuccess;
+  cfg.gridDim = dim3(grid_b);
+  cfg.dynamicSmemBytes = smem_b;
+  return cudaLaunchKernelEx(&cfg, ksearch, model->g, (const double4*)data->g.p64, (const double4*)data->g.nrm, nd,
+                            ctx->d_state.p, maxdist2, ctx->nn_cache.p, ctx->nn_budget.p, ctx->nn_pm.p,
+                            (const int*)ctx->queue.p, (const unsigned*)ctx->seg_count.p, (int)nseg, tiles_per_seg,
+                            ctx->partials.p, ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p,
+                            ctx->stage2_log.p, comm);
 }
 
 int launch_split_dispatch(b200icp_ctx* ctx, bool plane, bool exact, const b200icp_scan* model,
@@ -693,10 +708,13 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   CU_TRY(ctx->stage2_log.ensure(2 * (size_t)max_iter));
   CU_TRY(ctx->nn_cache.ensure(data->n));
   CU_TRY(ctx->nn_budget.ensure(data->n));
-  // two-kernel iteration (streaming pass + queued searches) for the point-to-point moment set when every point
-  // is visited every iteration; NAPX (44 moments) and rnd > 1 keep the single fused kernel
-  static const bool force_fused = getenv("B200ICP_FUSED") != nullptr;
-  const bool split = !napx && prm->rnd <= 1 && !force_fused;
+  // Two-kernel iteration (stream_kernels.cuh: TMA-streamed pass over every point + queued searches), available for
+  // the point-to-point moment set when every point is visited every iteration.  Opt-in (B200ICP_SPLIT=1): measured
+  // on the 1M/1M bench pair it is 2.6 % slower per match than the single fused kernel (8.46 vs 8.24 ms; faster
+  // only once < 20 % of the points still search, profiles/r01_split_vs_fused.md), so the fused kernel stays the
+  // default.  Read per call so that tests can exercise both paths in one process.
+  const char* env_split = getenv("B200ICP_SPLIT");
+  const bool split = !napx && prm->rnd <= 1 && env_split && env_split[0] == '1';
   if (split) {
     CU_TRY(ctx->nn_pm.ensure(data->n));
     CU_TRY(ctx->queue.ensure(((data->n + kBlock - 1) / kBlock) * kBlock));
@@ -827,6 +845,13 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   if (result) *result = res;
   return B200ICP_OK;
 }
+
+#ifdef B200_TIMING
+// debug builds only: the in-kernel timeline of the last iteration (globaltimer ns), see tl_mark
+int b200icp_debug_timing(unsigned long long* out32) {
+  return cudaMemcpyFromSymbol(out32, g_tl, 32 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2,
                          uint32_t* searches) {

@@ -16,6 +16,16 @@
 
 namespace b200 {
 
+// ---- optional in-kernel timeline (build with -DB200_TIMING; read with b200icp_debug_timing) ----------------
+#ifdef B200_TIMING
+__device__ unsigned long long g_tl[32];
+__device__ __forceinline__ void tl_mark(int k) {
+  if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tl[k] = t; }
+}
+#else
+__device__ __forceinline__ void tl_mark(int) {}
+#endif
+
 struct XfSmem {
   double X[16], Sinv[16], S[16], Nm[9], o[3];
   float dX[12];     // X - Xprev (rotation block + translation), fp32: per-iteration motion of a data point
@@ -159,17 +169,19 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // stage the loop state in shared memory: one coalesced read now, one coalesced write at the end, instead
   // of a single thread chasing ~100 dependent global accesses
+  tl_mark(8);
   for (int i = tid; i < kWords; i += kBlock)
     st_raw[i] = __ldcg(reinterpret_cast<const double*>(gst) + i);
   const int NS = moment_count(gst->algo);
   __syncthreads();   // scratch aliases the accumulators other warps may still be reading
+  tl_mark(9);
   // reduction: lane = moment, warp w takes blocks w, w+8, ... -> every load is one coalesced 184/352-byte row
   // of a block's partials; fixed shape, so the sums do not depend on timing
   for (int k0 = 0; k0 < NS; k0 += 32) {
     const int k = k0 + lane;
     double v = 0.0;
     if (k < NS) {
-#pragma unroll 8
+#pragma unroll 24   // the loads are independent: keep many in flight, this sits on the serial tail of the iteration
       for (int b = warp; b < nblocks; b += kWarps) v += __ldcg(partials + (size_t)b * NS_MAX + k);
       wpart[warp][k] = v;
     }
@@ -179,6 +191,7 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
     mom[tid] = ((wpart[0][tid] + wpart[1][tid]) + (wpart[2][tid] + wpart[3][tid])) +
                ((wpart[4][tid] + wpart[5][tid]) + (wpart[6][tid] + wpart[7][tid]));
   __syncthreads();
+  tl_mark(10);
   if (comm.world > 1) {
     // ---- fused all-reduce over NVLink peer memory (query-sharded match): this rank's moments are stored
     // straight into every rank's mailbox, a flag with the iteration's sequence number follows, and every
@@ -220,8 +233,10 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
     solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
   }
   __syncthreads();
+  tl_mark(11);
   for (int i = tid; i < kWords; i += kBlock)
     reinterpret_cast<double*>(gst)[i] = st_raw[i];
+  tl_mark(12);
 }
 
 

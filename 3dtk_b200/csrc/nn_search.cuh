@@ -44,7 +44,10 @@ constexpr int kMaxRows = 9;
 #define B200_SCAN_BATCH 2
 #endif
 constexpr int kScanBatch = B200_SCAN_BATCH;   // candidate loads kept in flight per lane
-constexpr int kBallRings = 8;   // thread-level ball scan covers cells up to this Chebyshev distance
+constexpr int kBallRings = 8;
+// (tried: prefetch.global.L1 of every range's cache lines once the ranges are known, so that the walk below hits --
+//  slower in every phase, 8.66 vs 8.24 ms per 1M/1M match: the kernel is issue-bound enough that the extra
+//  instructions cost more than the misses they hide)
 
 struct Best {
   double d2;      // exact (EXACT) or fp32 (fast) squared distance of the current best, init maxdist2
@@ -521,6 +524,7 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm,
             scan_range_exact(g, sm.rng[2 * k][tid], sm.rng[2 * k + 1][tid], qx, qy, qz, sx, sy, sz, e, b);
         }
       } else {
+        // (tried: a first pass with a 1.5-cell ball for unseeded queries -- slower, 1.22 vs 1.01 ms at iteration 0)
         const double kneed = ceil(rs * g.inv_h);
         const int kmax = (int)fmin(kneed, (double)kBallRings);
         float r2 = fminf(__double2float_ru(rs2), 3.0e38f) * 1.00001f + 1e-6f * hh;

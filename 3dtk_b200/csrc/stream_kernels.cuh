@@ -51,6 +51,31 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+// programmatic dependent launch: the next kernel of the stream may be scheduled while this one drains
+// (launch_dependents), and must not touch its predecessor's results before pdl_wait()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifndef B200_EVICT_FIRST
+#define B200_EVICT_FIRST 1
+#endif
+// L2 policy for the streamed arrays: they are read once per iteration and must not push the model grid (which the
+// latency-bound searches live on) out of the L2
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                                 unsigned long long pol) {
+#if B200_EVICT_FIRST
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol) : "memory");
+#else
+  tma_load_1d(dst, src, bytes, bar);
+#endif
+}
+
 constexpr int kStreamStages = 4;
 constexpr int kMaxSegments = 512;          // stream-kernel grid (= queue segments) upper bound
 
@@ -74,6 +99,10 @@ icp_stream_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
                   const IterState* __restrict__ st, double maxdist2, const double4* __restrict__ pm,
                   float* __restrict__ nn_budget, int* __restrict__ queue, unsigned* __restrict__ seg_count,
                   uint32_t tiles_per_seg, double* __restrict__ partials) {
+  if (blockIdx.x == 0) tl_mark(16);
+  pdl_wait();                 // the previous iteration's solve has published the pose
+  if (blockIdx.x == 0) tl_mark(17);
+  pdl_launch_dependents();    // the search kernel's blocks may take SM slots as they free up (they wait, too)
   if (st->done) return;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   StreamSmem& sm = *reinterpret_cast<StreamSmem*>(dyn_smem);
@@ -102,12 +131,13 @@ icp_stream_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
     mbar_fence_init();
   }
   __syncthreads();
+  const unsigned long long pol = l2_evict_first_policy();
   auto issue = [&](uint32_t tile, int stage) {   // one thread: arm the barrier, start the three bulk copies
     const size_t base = (size_t)tile * kBlock;
     mbar_arrive_expect_tx(&sm.full[stage], kStageBytes);
-    tma_load_1d(sm.st[stage].dq, dq + base, (unsigned)sizeof(sm.st[stage].dq), &sm.full[stage]);
-    tma_load_1d(sm.st[stage].pm, pm + base, (unsigned)sizeof(sm.st[stage].pm), &sm.full[stage]);
-    tma_load_1d(sm.st[stage].bud, nn_budget + base, (unsigned)sizeof(sm.st[stage].bud), &sm.full[stage]);
+    tma_load_1d_hint(sm.st[stage].dq, dq + base, (unsigned)sizeof(sm.st[stage].dq), &sm.full[stage], pol);
+    tma_load_1d_hint(sm.st[stage].pm, pm + base, (unsigned)sizeof(sm.st[stage].pm), &sm.full[stage], pol);
+    tma_load_1d_hint(sm.st[stage].bud, nn_budget + base, (unsigned)sizeof(sm.st[stage].bud), &sm.full[stage], pol);
   };
   auto is_full = [&](uint32_t tile) { return (size_t)(tile + 1) * kBlock <= (size_t)nd; };
   if (tid == 0)
@@ -165,7 +195,9 @@ icp_stream_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
     qn += total;
   }
   if (tid == 0) seg_count[blockIdx.x] = qn;
+  if (blockIdx.x == 0) tl_mark(18);
   block_reduce_store_regs<NS_P2P>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+  if (blockIdx.x == 0) tl_mark(19);
 }
 
 // dynamic shared memory of icp_search_kernel
@@ -184,6 +216,9 @@ icp_search_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
                   double* __restrict__ partials, unsigned* __restrict__ stage2_counter,
                   double* __restrict__ rms_log, unsigned long long* __restrict__ npairs_log,
                   unsigned* __restrict__ stage2_log, const __grid_constant__ CommDev comm) {
+  if (blockIdx.x == 0) tl_mark(0);
+  pdl_wait();                 // queue segments, budgets and stream partials are complete
+  if (blockIdx.x == 0) tl_mark(1);
   if (st->done) return;
   constexpr int NS = (int)NS_P2P;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -220,6 +255,7 @@ icp_search_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
   __syncthreads();
   const unsigned total = sm.seg_off[kMaxSegments];
   const unsigned seg_stride = tiles_per_seg * kBlock;
+  if (blockIdx.x == 0) tl_mark(2);
 
   PairCtx pc{&model, dn, &xf};
   unsigned stage2 = 0;
@@ -262,10 +298,13 @@ icp_search_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
     __syncwarp();
   }
 
-  double* const my_partials = partials + (size_t)(nseg + blockIdx.x) * NS_MAX;
-  block_reduce_store<NS>(acc, my_partials);
+  if (blockIdx.x == 0) tl_mark(3);
+  // blocks beyond the last batch accumulated nothing: their rows are left out of the reduction
+  const unsigned active_blocks = min((nbatch + kWarps - 1u) / kWarps, gridDim.x);
+  if (blockIdx.x < active_blocks) block_reduce_store<NS>(acc, partials + (size_t)(nseg + blockIdx.x) * NS_MAX);
   if (lane == 0 && stage2) atomicAdd(stage2_counter, stage2);
   if (blockIdx.x == 0 && tid == 0 && total) atomicAdd(stage2_counter + 1, total);
+  if (blockIdx.x == 0) tl_mark(4);
   // ---- the last block to get here reduces all partials (stream + search) and runs the solve
   __shared__ int is_last;
   __threadfence();
@@ -276,9 +315,13 @@ icp_search_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
     if (is_last) stage2_counter[2] = 0;   // ready for the next launch
   }
   __syncthreads();
+  // every block is past its searches: the next iteration's stream kernel may be scheduled (it waits for the
+  // solve below through griddepcontrol.wait, which only returns when this whole grid has finished)
+  pdl_launch_dependents();
   if (is_last) {
+    tl_mark(7);
     __threadfence();
-    solve_step(st, partials, nseg + (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
+    solve_step(st, partials, nseg + (int)active_blocks, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
   }
 }
 

@@ -236,7 +236,9 @@ def main():
               "max_iter": a.max_iter, "eps_icp": 1e-5, "exact_nn": bool(a.exact),
               "sharding": "one scan pair per GPU, no data-path collective" if a.shard == "pairs" else
                           "ONE pair; data points split across GPUs; moments all-reduced in-kernel over NVLink peer memory",
-              "l2": "flushed between steps (256 MiB write)"}
+              "l2": "flushed between steps (256 MiB write)",
+              "iteration_form": "two-kernel (B200ICP_SPLIT=1)" if os.environ.get("B200ICP_SPLIT", "0")[:1] == "1"
+                                else "fused kernel (default)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if a.impl == "reference":
@@ -400,15 +402,34 @@ def main():
     hbm_peak, peak_src = peaks()
     n_occ = ginfo["n_occupied"]
     b_alg = 16.0 * n + 16.0 * n + 8.0 * n_occ + 512.0
-    achieved = b_alg / (nn_ms * 1e-3) / 1e9 if nn_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "icp_iter_kernel<P2P,POINT,%s>" % ("EXACT" if a.exact else "FP32"),
+    split = os.environ.get("B200ICP_SPLIT", "0")[:1] == "1"
+    if split:
+        # opt-in two-kernel form: one ICP iteration = icp_stream_kernel (every point, TMA-streamed) + icp_search_kernel
+        # (queued exact searches + solve).  B_alg is per iteration, so it is divided by both launches.
+        stream_ms = solve_ms
+        iter_ms = nn_ms + stream_ms
+        kname = "icp_search_kernel<POINT,%s> (+ icp_stream_kernel: one ICP iteration = 2 launches)"
+    else:
+        stream_ms = None
+        iter_ms = nn_ms
+        kname = "icp_iter_kernel<P2P,POINT,%s>"
+    achieved = b_alg / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": kname % ("EXACT" if a.exact else "FP32"),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": ncu_traffic()[0],
                 "traffic_source": (ncu_traffic()[1] or {}).get("source"),
-                "algorithmic_bytes_per_launch": b_alg, "kernel_ms": nn_ms, "solve_kernel_ms": solve_ms,
+                "algorithmic_bytes_per_launch": b_alg, "kernel_ms": nn_ms, "iteration_ms": iter_ms,
                 "peak_source": peak_src,
-                "note": "B_alg = 16*N_d + 16*N_m + 8*N_occupied_cells + 512 (SURVEY 8d); model fits L2, the "
-                        "kernel is L1/L2-latency and issue bound, see DESIGN.md"}
+                "note": "B_alg = 16*N_d + 16*N_m + 8*N_occupied_cells + 512 per ICP iteration (SURVEY 8d); the "
+                        "kernel is bound by L1/L2 latency and instruction issue of the candidate scan, not by HBM "
+                        "(model + tables fit the 126 MB L2), see DESIGN.md section 4"}
+    if split:
+        stream_bytes = 72.0 * n_data   # d0 32 B + cached neighbour 32 B + budget 4 B read, budget 4 B written
+        roofline["stream_kernel"] = {
+            "bound": "hbm", "kernel_ms": stream_ms, "bytes_per_launch": stream_bytes,
+            "achieved": stream_bytes / (stream_ms * 1e-3) / 1e9 if stream_ms > 0 else None,
+            "frac": stream_bytes / (stream_ms * 1e-3) / 1e9 / hbm_peak if stream_ms > 0 else None,
+            "note": "mean over all iterations of the match, launch overhead included"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong" if shard_q else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,

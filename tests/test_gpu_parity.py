@@ -104,8 +104,16 @@ def test_get_pt_pairs_sums_and_plane_projection(icp, ctx, ref):
 
 
 # ------------------------------------------------------------------ fused match vs oracle match
+@pytest.fixture(params=["fused", "split"])
+def iteration_form(request, monkeypatch):
+    """Both device forms of one ICP iteration: the single fused kernel (default) and the two-kernel form
+    (TMA-streamed pass + queued searches, stream_kernels.cuh), selected per call by B200ICP_SPLIT."""
+    monkeypatch.setenv("B200ICP_SPLIT", "1" if request.param == "split" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("algo", [1, 2, 6])
-def test_match_point_to_point_vs_oracle(icp, ctx, algo):
+def test_match_point_to_point_vs_oracle(icp, ctx, algo, iteration_form):
     model, data, Ptrue = make_pair(icp, 60000, 50000)
     want = orclib.port_match(model, data, algo=algo, max_dist=25.0, max_iter=50, eps=1e-5)
     m, d = icp.Scan(ctx, model, max_dist_hint=25.0), icp.Scan(ctx, data, max_dist_hint=25.0)
@@ -131,7 +139,7 @@ def test_match_fast_mode_within_north_star_tolerance(icp, ctx):
 
 
 @pytest.mark.parametrize("algo", [10, 1])
-def test_match_point_to_plane_vs_oracle(icp, ctx, algo):
+def test_match_point_to_plane_vs_oracle(icp, ctx, algo, iteration_form):
     model, data, Ptrue = make_pair(icp, 40000, 30000, theta_deg=(0.3, -0.5, 0.4), pos=(6.0, -3.0, 2.0))
     nrm = icp.normals_knn(ctx, data, 10, np.array([0.0, 150.0, 0.0]))
     want = orclib.port_match(model, data, nrm, algo=algo, mode=2, max_dist=25.0, max_iter=30, eps=1e-5)
@@ -149,7 +157,7 @@ def test_match_point_to_plane_vs_oracle(icp, ctx, algo):
     np.testing.assert_allclose(n2, want["nrm"], rtol=0, atol=1e-9)  # normals follow transform3normal
 
 
-def test_match_with_moved_model_and_sequential_roles(icp, ctx):
+def test_match_with_moved_model_and_sequential_roles(icp, ctx, iteration_form):
     """scan1 is matched to scan0 and then serves as the model for scan2 (its tree stays in the original
     frame, queries go through inv(dalignxf) -- 'fast corresponding points', scan.cc:1208-1240)."""
     a = icp.synth_scene(7, 10, 30000, 0.5)
@@ -196,7 +204,7 @@ def test_edge_cases(icp, ctx):
         icp.icp6D(ctx, max_dist_match=-1.0)
 
 
-def test_match_is_deterministic(icp, ctx):
+def test_match_is_deterministic(icp, ctx, iteration_form):
     model, data, _ = make_pair(icp, 40000, 40000)
     outs = []
     for _ in range(2):
@@ -207,7 +215,7 @@ def test_match_is_deterministic(icp, ctx):
 
 
 # ------------------------------------------------------------------ full-size properties (1M points)
-def test_full_size_properties(icp, ctx):
+def test_full_size_properties(icp, ctx, iteration_form):
     n = 1_000_000
     model, data, Ptrue = make_pair(icp, n, n)
     m, d = icp.Scan(ctx, model, max_dist_hint=25.0), icp.Scan(ctx, data, max_dist_hint=25.0)

@@ -35,5 +35,5 @@ for _ in range(a.repeat):
 p = r["profile"]
 print(json.dumps({"points": n, "exact": a.exact, "grid": m.grid_info(), "iters": r["iterations_run"],
                   "nn_ms": [round(x, 4) for x in p["nn_ms"]], "stage2": [int(x) for x in p["stage2"]], "searches": [int(x) for x in p["searches"]],
-                  "nn_ms_mean": float(np.mean(p["nn_ms"])), "solve_ms_mean": float(np.mean(p["solve_ms"])),
+                  "stream_ms": [round(x, 4) for x in p["solve_ms"]], "nn_ms_mean": float(np.mean(p["nn_ms"])), "solve_ms_mean": float(np.mean(p["solve_ms"])),
                   "rms_last": float(r["rms"][-1])}))
