@@ -18,7 +18,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def icp():
     """The product binding; building the library first if it is missing (nvcc cross-compiles)."""
-    build = importlib.import_module("3dtk_b200.build")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b200icp_build", os.path.join(ROOT, "3dtk_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)   # by path: the package __init__ raises without the library
+    spec.loader.exec_module(build)
     build.build()
     return importlib.import_module("3dtk_b200")
 
