@@ -80,6 +80,11 @@ def _load():
         "b200icp_comm_destroy": (i32, [vp]),
         "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
+        "b200icp_graph_from_poses": (i32, [dp, i32, f64, i32, dp, i32, C.POINTER(i32)]),
+        "b200icp_lum_fill_gb": (i32, [vp, dp, i32, dp, i32, f64, dp, dp, dp]),
+        "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64)]),
+        "b200icp_lum_graph_slam": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, C.POINTER(f64), C.POINTER(i32)]),
+        "b200icp_matrix4_to_euler": (None, [dp, dp, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_reduce_octree_center": (i32, [vp, dp, sz, f64, dp, C.POINTER(sz)]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
@@ -329,6 +334,78 @@ def lum_link(ctx, first, second, max_dist_match2):
     Cm, CD, n = np.zeros(36), np.zeros(6), C.c_uint64(0)
     _check(lib.b200icp_lum_link(ctx._h, first._h, second._h, max_dist_match2, _ptr(Cm), _ptr(CD), C.byref(n)))
     return Cm.reshape(6, 6), CD, n.value
+
+
+def matrix4_to_euler(m):
+    """Matrix4ToEuler (globals.icc:540-578) -> (rPos[3], rPosTheta[3])"""
+    m = _f64(m).reshape(16)
+    th, pos = np.empty(3), np.empty(3)
+    lib.b200icp_matrix4_to_euler(_ptr(m), _ptr(th), _ptr(pos))
+    return pos, th
+
+
+def _scan_array(scans):
+    return (C.c_void_p * len(scans))(*[s._h for s in scans])
+
+
+class Graph:
+    """Graph (src/slam6d/graph.cc): list of (from, to) links between scan numbers."""
+
+    def __init__(self, links, n_scans):
+        self.links = np.ascontiguousarray(links, dtype=np.int32).reshape(-1, 2)
+        self.n_scans = int(n_scans)
+
+    @classmethod
+    def from_poses(cls, rpos, cldist2, loopsize):
+        """Graph(int nodes, double cldist2, int loopsize), graph.cc:108-127"""
+        rpos = _f64(rpos, 3)
+        n = C.c_int(0)
+        _check(lib.b200icp_graph_from_poses(_ptr(rpos), rpos.shape[0], cldist2, loopsize, None, 0, C.byref(n)))
+        links = np.zeros((max(n.value, 1), 2), dtype=np.int32)
+        _check(lib.b200icp_graph_from_poses(_ptr(rpos), rpos.shape[0], cldist2, loopsize, _ptr(links), n.value,
+                                            C.byref(n)))
+        return cls(links[:n.value], rpos.shape[0])
+
+    def get_nr_links(self):
+        return self.links.shape[0]
+
+
+class lum6DEuler:
+    """lum6DEuler (src/slam6d/lum6Deuler.cc): global relaxation over a graph of scans resident on the device."""
+
+    def __init__(self, ctx, max_dist_match_lum=25.0, epsilon_lum=0.5):
+        self.ctx = ctx
+        self.max_dist_match2_lum = float(max_dist_match_lum) ** 2     # graphSlam6D.cc:60: squared once
+        self.epsilon_lum = float(epsilon_lum)
+
+    def fill_gb(self, graph, scans, G=None, B=None, link_subset=None):
+        """FillGB3D over `link_subset` (indices into graph.links; default all) -> (G, B, npairs per link)"""
+        dim = 6 * (len(scans) - 1)
+        G = np.zeros((dim, dim)) if G is None else G
+        B = np.zeros(dim) if B is None else B
+        links = graph.links if link_subset is None else graph.links[list(link_subset)]
+        links = np.ascontiguousarray(links, dtype=np.int32)
+        npairs = np.zeros(max(links.shape[0], 1), dtype=np.uint64)
+        _check(lib.b200icp_lum_fill_gb(self.ctx._h, _scan_array(scans), len(scans), _ptr(links), links.shape[0],
+                                       self.max_dist_match2_lum, _ptr(G), _ptr(B), _ptr(npairs)))
+        return G, B, npairs[:links.shape[0]]
+
+    @staticmethod
+    def solve_update(scans, G, B):
+        """X = G^-1 B, pose corrections, Scan::transformToEuler -> sum of position differences"""
+        s = C.c_double(0.0)
+        G, B = _f64(G), _f64(B)
+        _check(lib.b200icp_lum_solve_update(_scan_array(scans), len(scans), _ptr(G), _ptr(B), C.byref(s)))
+        return s.value
+
+    def doGraphSlam6D(self, graph, scans, nr_it):
+        """lum6DEuler::doGraphSlam6D -> (ret, iterations run)"""
+        ret, it = C.c_double(0.0), C.c_int(0)
+        links = np.ascontiguousarray(graph.links, dtype=np.int32)
+        _check(lib.b200icp_lum_graph_slam(self.ctx._h, _scan_array(scans), len(scans), _ptr(links), links.shape[0],
+                                          self.max_dist_match2_lum, int(nr_it), self.epsilon_lum, C.byref(ret),
+                                          C.byref(it)))
+        return ret.value, it.value
 
 
 def reduce_octree_center(ctx, xyz, voxel_size):

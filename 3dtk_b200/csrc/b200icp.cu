@@ -268,6 +268,8 @@ int launch_split_dispatch(b200icp_ctx* ctx, bool plane, bool exact, const b200ic
 extern "C" {
 
 const char* b200icp_last_error(void) { return g_last_error.c_str(); }
+// internal: lets the library's other translation units (lum_graph.cpp) report through the same channel
+int b200icp_set_error_(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 
 const char* b200icp_version(void) {
   return "b200icp 0.1 (sm_100a; exact fp64-verified grid NN; fused match; no CPU fallback)";
@@ -845,6 +847,15 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   if (result) *result = res;
   return B200ICP_OK;
 }
+
+#ifdef B200_TILE_STATS
+// debug builds only: counters of the cooperative tile search (batches tiled, staged points, batches refused); reset on read
+int b200icp_debug_tile_stats(unsigned long long* out8) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out8, g_tile_stats, sizeof z) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(g_tile_stats, z, sizeof z) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 #ifdef B200_TIMING
 // debug builds only: the in-kernel timeline of the last iteration (globaltimer ns), see tl_mark

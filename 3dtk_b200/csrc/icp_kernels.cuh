@@ -241,6 +241,10 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
 
 
 constexpr int kQueueCap = 64;  // per-warp queue of queries waiting for a full search
+#ifndef B200_TILE_SPAN
+#define B200_TILE_SPAN 96
+#endif
+constexpr int kTileSpan = B200_TILE_SPAN;   // a batch whose queries span at most this many rows of the data scan is "dense"
 
 // dynamic shared memory of icp_iter_kernel
 template <int NS>
@@ -398,7 +402,10 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     double bd2;
     unsigned boidx;
     float newbud;
-    nn_warp_search<EXACT>(model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2);
+    // neighbours in the data scan's cell order -> overlapping stencils -> cooperative tile search
+    const bool dense = nb == 32 && (unsigned)(list[31] - list[0]) <= (unsigned)kTileSpan;
+    nn_warp_search<EXACT>(model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2,
+                          dense);
     if (on) {
       nn_cache[i] = bj;
       nn_budget[i] = newbud;
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(kBlock)
 nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* __restrict__ q_nrm,
                 size_t n, const double* __restrict__ xfs, double maxdist2, int32_t* __restrict__ idx_out,
                 double* __restrict__ d2_out, double* __restrict__ partials) {
-  __shared__ SearchSmem sm;
+  __shared__ SearchSmemSmall sm;
   __shared__ double S[16], Sinv[16];
   const int tid = threadIdx.x;
   if (tid < 16) { S[tid] = xfs[tid]; Sinv[tid] = xfs[16 + tid]; }
@@ -563,7 +570,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kBlock, 2)
 lum_link_kernel(GridDev model, const double4* __restrict__ dq, uint32_t nd, const double* __restrict__ xfs,
                 double maxdist2, int* __restrict__ nn_cache, double* __restrict__ partials) {
-  __shared__ SearchSmem sm;
+  __shared__ SearchSmemSmall sm;
   __shared__ double X[16], S[16], Sinv[16], D[6];
   const int tid = threadIdx.x;
   if (tid < 16) { X[tid] = xfs[tid]; S[tid] = xfs[16 + tid]; Sinv[tid] = xfs[32 + tid]; }

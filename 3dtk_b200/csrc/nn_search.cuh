@@ -62,10 +62,44 @@ struct Cand {     // fp32 tracking state of the inner loops
   int j1;         // position of the smallest
 };
 
-// thread-private columns: rng[k][tid]
-struct SearchSmem {
-  unsigned rng[2 * kMaxRows][kBlock];
+// thread-private columns: rng[k][tid].  The 32 columns of a warp double as that warp's candidate TILE (see
+// "tile" in the header comment): row k of the warp's slice holds 8 float4 points (128 B), so the tile never
+// touches another warp's columns and no block barrier is needed between the two uses.
+#ifndef B200_RNG_ROWS
+#define B200_RNG_ROWS 18
+#endif
+constexpr int kRngRows = B200_RNG_ROWS > 2 * kMaxRows ? B200_RNG_ROWS : 2 * kMaxRows;
+// Off by default: measured slower on the bench pair (profiles/r01_tile_search_experiment.md) -- the union of 32
+// neighbouring stencils is ~270 points, so evaluating all of it from shared memory costs as many instructions
+// as the divergent per-lane walks it replaces, and the staging adds a serial chain of shuffles and loads.
+#ifndef B200_TILE
+#define B200_TILE 0
+#endif
+#ifndef B200_TILE_MIN_LANES
+#define B200_TILE_MIN_LANES 12
+#endif
+template <int ROWS>
+struct SearchSmemT {
+  static constexpr int kTileCap = ROWS * 8;    // candidate points a warp can stage
+  unsigned rng[ROWS][kBlock];
 };
+using SearchSmem = SearchSmemT<kRngRows>;            // iteration kernels (dynamic shared memory)
+using SearchSmemSmall = SearchSmemT<2 * kMaxRows>;   // kernels with a static table (API batch search, LUM link)
+
+// optional counters of the tile path (build with -DB200_TILE_STATS; read with b200icp_debug_tile_stats)
+__device__ unsigned long long g_tile_stats[8];
+__device__ __forceinline__ void tile_stat(int k, unsigned long long v) {
+#ifdef B200_TILE_STATS
+  if ((threadIdx.x & 31) == 0) atomicAdd(&g_tile_stats[k], v);
+#endif
+}
+
+template <class SM>
+__device__ __forceinline__ float4* tile_row(SM& sm, int k) {
+  return reinterpret_cast<float4*>(&sm.rng[k][threadIdx.x & ~31]);
+}
+template <class SM>
+__device__ __forceinline__ float4* tile_slot(SM& sm, int s) { return tile_row(sm, s >> 3) + (s & 7); }
 
 template <bool EXACT>
 __device__ __forceinline__ float filter_bound(double b, float e) {
@@ -143,7 +177,8 @@ __device__ __forceinline__ void best_merge(Best& b, double od2, int oj, unsigned
 // flattened fp32 scan of the first `nrows` ranges of this thread's table.  Candidates are taken four at
 // a time: their indices come from the (cheap) range walk, then four independent 16-byte loads are in
 // flight before the first distance is needed -- the loop is bound by load latency, not arithmetic.
-__device__ __forceinline__ void scan_rows(const GridDev& g, const SearchSmem& sm, int nrows, float qx,
+template <class SM>
+__device__ __forceinline__ void scan_rows(const GridDev& g, const SM& sm, int nrows, float qx,
                                           float qy, float qz, Cand& c) {
   const int tid = threadIdx.x;
   int r = 0;
@@ -197,23 +232,19 @@ __device__ __forceinline__ void cand_seed(const GridDev& g, const Best& b, float
   if (b.j >= 0) { c.d1 = dist32(__ldg(g.p32 + b.j), qx, qy, qz); c.j1 = b.j; }
 }
 
-// fp32 scan of the part of the 3x3x3 stencil that the ball of squared radius r2 (already inflated for
-// fp32 rounding) touches.  Leaves the ranges in the thread's table (`nrows` of them) and the tracking
-// state in `c` (seeded with b's point).  rc2 = squared distance from the query to the nearest cell that
-// was NOT scanned (at most h^2: the edge of the stencil) -- everything closer than that was seen, which
+// The part of the 3x3x3 stencil that the ball of squared radius r2 (already inflated for fp32 rounding)
+// touches, as up to nine x-runs [va[r], vb[r]) of the cell-sorted point array (va == vb: row not needed or
+// empty; all range loads are issued together).  rc2 = squared distance from the query to the nearest cell
+// that is NOT covered (at most h^2: the edge of the stencil) -- everything closer than that is covered, which
 // certifies a radius that is usually much larger than the ball that was asked for.
-__device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz,
-                                            float fx, float fy, float fz, float qx, float qy, float qz,
-                                            float r2, const Best& b, Cand& c, float& rc2) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void stencil_ranges(const GridDev& g, int cx, int cy, int cz, float fx, float fy,
+                                               float fz, float r2, unsigned (&va)[9], unsigned (&vb)[9],
+                                               float& rc2) {
   const float h = (float)g.h;
   const float lo_y = fy * fy, hi_y = (h - fy) * (h - fy);
   const float lo_z = fz * fz, hi_z = (h - fz) * (h - fz);
   const float lo_x = fx * fx, hi_x = (h - fx) * (h - fx);
   rc2 = h * h;
-  // pass 1: which rows / x-ends the ball touches, and all their range loads issued together
-  unsigned va[9], vb[9];
-  bool use[9];
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     const int dy = (r % 3) - 1, dz = (r / 3) - 1;
@@ -221,7 +252,6 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, in
     const float dyz2 = (dy < 0 ? lo_y : (dy > 0 ? hi_y : 0.f)) + (dz < 0 ? lo_z : (dz > 0 ? hi_z : 0.f));
     const float rem = r2 - dyz2;
     const bool left = lo_x <= rem, right = hi_x <= rem;
-    use[r] = false;
     va[r] = vb[r] = 0;
     if (rem < 0.f) { rc2 = fminf(rc2, dyz2); continue; }          // whole row left out
     if (!left) rc2 = fminf(rc2, dyz2 + lo_x);                      // its -x / +x ends left out
@@ -232,14 +262,23 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, in
       const size_t row = ((size_t)z * g.ny + y) * g.nx;
       va[r] = __ldg(g.cell_start + row + x0);
       vb[r] = __ldg(g.cell_start + row + x1 + 1);
-      use[r] = true;
     }
   }
-  // pass 2: compact the non-empty ranges into the thread's table
+}
+
+// fp32 scan of those runs by the query's own thread.  Leaves the non-empty ranges in the thread's table
+// (`nrows` of them) and the tracking state in `c` (seeded with b's point).
+template <class SM>
+__device__ __forceinline__ int stencil_scan(const GridDev& g, SM& sm, int cx, int cy, int cz,
+                                            float fx, float fy, float fz, float qx, float qy, float qz,
+                                            float r2, const Best& b, Cand& c, float& rc2) {
+  const int tid = threadIdx.x;
+  unsigned va[9], vb[9];
+  stencil_ranges(g, cx, cy, cz, fx, fy, fz, r2, va, vb, rc2);
   int nrows = 0;
 #pragma unroll
   for (int r = 0; r < 9; ++r)
-    if (use[r] && va[r] < vb[r]) {
+    if (va[r] < vb[r]) {
       sm.rng[2 * nrows][tid] = va[r];
       sm.rng[2 * nrows + 1][tid] = vb[r];
       ++nrows;
@@ -247,6 +286,86 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SearchSmem& sm, in
   cand_seed(g, b, qx, qy, qz, c);
   scan_rows(g, sm, nrows, qx, qy, qz, c);
   return nrows;
+}
+
+// ---- tile (warp-cooperative form of stage 1) --------------------------------------------------------
+// When the 32 queries of a batch are neighbours in the data scan's cell order, their stencils overlap almost
+// completely: each model point is wanted by ~10 lanes.  Instead of every lane walking its own runs through
+// L1/L2, the warp stages the UNION of the runs once in its slice of shared memory (coalesced-ish 16-byte
+// loads, each point fetched once) and every lane then evaluates every staged point from shared memory with
+// broadcast reads: no divergence, no dependent global loads in the loop.  A lane sees candidates outside its own
+// runs as well; they lie outside its ball, so they can only tighten the runner-up bound (conservative) or
+// raise an fp32 ambiguity that the exact rescan of the lane's own runs settles -- the result is unchanged.
+//
+// Union: per stencil slot r, lane l stages [max(a_l, M_l), b_l) where M_l = max b over the earlier lanes,
+// provided a_l >= a_k of the lane k that set M_l (then [a_l, M_l) lies inside k's run, which is staged by
+// induction); otherwise it stages its whole run.  A point staged twice (irregular order, or the same model
+// row reached through different slots by lanes of different cell rows) is harmless: a repeat of the current
+// best is skipped by index, a repeat of anything else leaves (d1, d2nd) unchanged.
+// Returns false (nothing consumed) when the union does not fit the tile.
+__device__ __forceinline__ unsigned long long warp_excl_max_u64(unsigned long long v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d && o > v) v = o;
+  }
+  const unsigned long long e = __shfl_up_sync(0xffffffffu, v, 1);
+  return lane == 0 ? 0ull : e;
+}
+
+template <class SM>
+__device__ __forceinline__ bool tile_stage(const GridDev& g, SM& sm, const unsigned (&va)[9],
+                                           const unsigned (&vb)[9], int& T_out) {
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  __syncwarp();   // the lanes' table columns are about to be overwritten by other lanes
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const bool has = va[r] < vb[r];
+    const unsigned a = has ? va[r] : 0xFFFFFFFFu, b = has ? vb[r] : 0u;
+    const unsigned long long pk = warp_excl_max_u64(((unsigned long long)b << 32) | (unsigned)(~a), lane);
+    const unsigned M = (unsigned)(pk >> 32), aK = ~(unsigned)pk;
+    unsigned from = a;
+    if (has && M != 0u && a >= aK) from = max(a, M);
+    const int n = has && b > from ? (int)(b - from) : 0;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (base + total > SM::kTileCap) { __syncwarp(); return false; }   // warp-uniform
+    int off = base + incl - n;
+    for (unsigned j = from; j < from + (unsigned)n; ++j, ++off) {
+      float4 p = __ldg(g.p32 + j);
+      p.w = __int_as_float((int)j);
+      *tile_slot(sm, off) = p;
+    }
+    base += total;
+  }
+  // pad to whole rows of 8 with points at infinity (never the best, never the runner-up)
+  const int T8 = (base + 7) & ~7;
+  if (base + lane < T8) *tile_slot(sm, base + lane) = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000),
+                                                                   __int_as_float(0x7f800000), __int_as_float(-1));
+  __syncwarp();
+  T_out = T8;
+  return true;
+}
+
+// every lane evaluates every staged point (c enters seeded)
+template <class SM>
+__device__ __forceinline__ void tile_scan(SM& sm, int T8, float qx, float qy, float qz, Cand& c) {
+  const float4* row = tile_row(sm, 0);
+  for (int k = 0; k < T8; k += 8, row += kBlock / 4) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 p = row[u];
+      const float d = dist32(p, qx, qy, qz);
+      const int j = __float_as_int(p.w);
+      if (j != c.j1) cand_update(c, d, j);
+    }
+  }
 }
 
 // ---- stage 1b ------------------------------------------------------------------------------------
@@ -259,7 +378,8 @@ __device__ __forceinline__ float slab_dist(int d, float f, float h) {
 // Thread-level fp32 scan of a ball wider than a cell: covers the cells within `kmax` (<= kBallRings) of
 // the query's cell.  r2 = initial squared search radius (inflated); the ball shrinks to
 // (dist(best) + 2*delta)^2 as candidates appear.  On return r2 is the final (inflated) radius.
-__device__ __forceinline__ void ball_scan(const GridDev& g, SearchSmem& sm, int cx, int cy, int cz, float fx,
+template <class SM>
+__device__ __forceinline__ void ball_scan(const GridDev& g, SM& sm, int cx, int cy, int cz, float fx,
                                           float fy, float fz, float qx, float qy, float qz, float e,
                                           float delta, int kmax, const Best& b, float& r2, Cand& c) {
   const int tid = threadIdx.x;
@@ -462,16 +582,162 @@ __device__ __forceinline__ float motion_budget(const Best& b, const Cand& c, flo
   return bud > 0.0 ? __double2float_rd(bud) : 0.f;
 }
 
+#if B200_TILE
+// ---- variant with the cooperative tile form of stage 1 (experiment, see B200_TILE above)
 // Warp-synchronous search: every lane of every warp calls this once per tile (it contains warp
 // collectives, no block barrier).  `active` lanes carry a query s (in the grid's frame); seed_j is the
 // sorted position of the neighbour found for this query last time (-1: none); delta >= 0 asks for a
 // motion budget (see header).  budget_out = certified budget (0 when none could be certified).
-template <bool EXACT>
-__device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm, bool active, double sx,
+// `dense`: (warp-uniform hint) the batch's queries are close together in the data scan's cell order, so the
+// cooperative tile form of stage 1 is worth trying.
+template <bool EXACT, class SM>
+__device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool active, double sx,
                                                double sy, double sz, double maxdist2, int seed_j,
                                                float delta, int& out_j, double& out_d2,
                                                unsigned& out_oidx, float& budget_out,
-                                               unsigned& stage2_count) {
+                                               unsigned& stage2_count, bool dense = false) {
+  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+  Best b;
+  b.d2 = maxdist2;
+  b.j = -1;
+  b.oidx = kNoIdx;
+  b.thr = 0.f;
+  bool need2 = false;
+  float qx = 0.f, qy = 0.f, qz = 0.f, e = 0.f;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  int cx = 0, cy = 0, cz = 0;
+  int cls = 0;          // 0: nothing to scan, 1: ball inside the stencil's guaranteed radius, 2: wider ball
+  double rs = 0.0, rs2 = 0.0;
+  const float hh = (float)(g.h * g.h);
+  budget_out = 0.f;
+  if (active) {
+    const double ox = fmax(fmax(g.bbox_lo[0] - sx, sx - g.bbox_hi[0]), 0.0);
+    const double oy = fmax(fmax(g.bbox_lo[1] - sy, sy - g.bbox_hi[1]), 0.0);
+    const double oz = fmax(fmax(g.bbox_lo[2] - sz, sz - g.bbox_hi[2]), 0.0);
+    const double dbox2 = ox * ox + oy * oy + oz * oz;
+    if (dbox2 < maxdist2) {  // false for NaN queries as well
+      qx = (float)(sx - g.c[0]); qy = (float)(sy - g.c[1]); qz = (float)(sz - g.c[2]);
+      e = query_err(qx, qy, qz, g.bmax);
+      cx = cell_coord(sx, g.g0[0], g.inv_h);
+      cy = cell_coord(sy, g.g0[1], g.inv_h);
+      cz = cell_coord(sz, g.g0[2], g.inv_h);
+      // offsets of the query inside its cell (meaningful also for queries outside the grid)
+      fx = (float)((sx - g.g0[0]) - (double)cx * g.h);
+      fy = (float)((sy - g.g0[1]) - (double)cy * g.h);
+      fz = (float)((sz - g.g0[2]) - (double)cz * g.h);
+      if (seed_j >= 0 && (unsigned)seed_j < g.n) {
+        const double ds = EXACT ? exact_d2(g, seed_j, sx, sy, sz)
+                                : (double)dist32(__ldg(g.p32 + seed_j), qx, qy, qz);
+        if (ds < maxdist2) { b.d2 = ds; b.j = seed_j; b.oidx = __float_as_uint(__ldg(g.p32 + seed_j).w); }
+      }
+      const double rg2 = g.h * g.h * (1.0 - 1e-9);
+      rs = sqrt(b.d2) + 2.0 * (double)delta;     // radius to certify
+      rs2 = rs * rs;
+      cls = rs2 <= rg2 ? 1 : 2;
+    } else {
+      // farther than maxdist from the model's bounding box: nothing can pair until it comes closer
+      const double slack = sqrt(dbox2) * (1.0 - 1e-9) - sqrt(maxdist2) * (1.0 + 1e-12);
+      if (slack > 0.0 && slack < 1.0e30) budget_out = __double2float_rd(slack);
+    }
+  }
+  const float r2 = fminf(__double2float_ru(rs2), 3.0e38f) * 1.00001f + 1e-6f * hh;   // inflated for fp32 rounding
+  Cand c;
+  c.d1 = 3.0e38f; c.d2nd = 3.0e38f; c.j1 = -1;
+  float rc2 = 0.f;
+  bool tiled = false;
+#if B200_TILE
+  if (dense && __popc(__ballot_sync(0xffffffffu, cls == 1)) >= B200_TILE_MIN_LANES) {
+    unsigned va[9], vb[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) va[r] = vb[r] = 0;
+    if (cls == 1) stencil_ranges(g, cx, cy, cz, fx, fy, fz, r2, va, vb, rc2);
+    int T8 = 0;
+    tiled = tile_stage(g, sm, va, vb, T8);
+    if (tiled) {
+      if (cls == 1) cand_seed(g, b, qx, qy, qz, c);
+      tile_scan(sm, T8, qx, qy, qz, c);
+      __syncwarp();   // the tile is dead from here on; lanes may reuse their table columns
+      tile_stat(0, 1); tile_stat(1, (unsigned long long)T8);
+    } else {
+      tile_stat(2, 1);
+    }
+  }
+#endif
+  if (cls == 1) {
+    // the ball fits inside the stencil's guaranteed radius: stage 1 alone is exact
+    int nrows = -1;
+    if (!tiled) nrows = stencil_scan(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, r2, b, c, rc2);
+    // certified radius: the requested ball, or better the (de-inflated) reach of the scanned cells
+    const float rcert2 = fmaxf(__double2float_rd(rs2), rc2 * 0.99999f - 2e-6f * hh);
+    const bool settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
+    if (!settled) {  // rare: two contenders closer than the fp32 error -> settle in fp64 over the lane's own runs
+      b.thr = filter_bound<true>(b.d2, e);
+      if (nrows >= 0) {
+        for (int k = 0; k < nrows; ++k)
+          scan_range_exact(g, sm.rng[2 * k][tid], sm.rng[2 * k + 1][tid], qx, qy, qz, sx, sy, sz, e, b);
+      } else {
+        unsigned va[9], vb[9];
+        float unused;
+        stencil_ranges(g, cx, cy, cz, fx, fy, fz, r2, va, vb, unused);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) scan_range_exact(g, va[r], vb[r], qx, qy, qz, sx, sy, sz, e, b);
+      }
+    }
+    if (settled) budget_out = motion_budget(b, c, e, rcert2, maxdist2);
+  } else if (cls == 2) {
+    // (tried: a first pass with a 1.5-cell ball for unseeded queries -- slower, 1.22 vs 1.01 ms at iteration 0)
+    const double kneed = ceil(rs * g.inv_h);
+    const int kmax = (int)fmin(kneed, (double)kBallRings);
+    float rb2 = r2;
+    const Best seed = b;
+    ball_scan(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, e, delta, kmax, b, rb2, c);
+    const bool settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
+    // certified radius: the final ball, de-inflated, but never more than the scanned rings cover
+    const float cover = (float)kmax * (float)g.h;
+    const float rcert2 = fminf(fmaxf(rb2 - 1e-6f * hh, 0.f) * 0.99997f, cover * cover * 0.99999f);
+    if (!settled) { b = seed; need2 = true; }                       // fp32-ambiguous winner
+    else if (kneed > (double)kBallRings) {                          // ball wider than the scan covers
+      const double cv = (double)kmax * g.h;
+      need2 = !(b.j >= 0 && b.d2 <= cv * cv * (1.0 - 1e-9));
+    }
+    if (settled && !need2) budget_out = motion_budget(b, c, e, rcert2, maxdist2);
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, need2);
+  stage2_count += lane == 0 ? __popc(todo) : 0;
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    Best wb;
+    wb.d2 = __shfl_sync(0xffffffffu, b.d2, src);
+    wb.j = __shfl_sync(0xffffffffu, b.j, src);
+    wb.oidx = __shfl_sync(0xffffffffu, b.oidx, src);
+    wb.thr = 0.f;
+    const double wsx = __shfl_sync(0xffffffffu, sx, src), wsy = __shfl_sync(0xffffffffu, sy, src),
+                 wsz = __shfl_sync(0xffffffffu, sz, src);
+    const float wqx = __shfl_sync(0xffffffffu, qx, src), wqy = __shfl_sync(0xffffffffu, qy, src),
+                wqz = __shfl_sync(0xffffffffu, qz, src), we = __shfl_sync(0xffffffffu, e, src);
+    const int wcx = __shfl_sync(0xffffffffu, cx, src), wcy = __shfl_sync(0xffffffffu, cy, src),
+              wcz = __shfl_sync(0xffffffffu, cz, src);
+    ring_search_warp<EXACT>(g, wcx, wcy, wcz, wqx, wqy, wqz, wsx, wsy, wsz, we, wb);
+    if (lane == src) { b.d2 = wb.d2; b.j = wb.j; b.oidx = wb.oidx; }
+  }
+  out_j = b.j;
+  out_d2 = b.d2;
+  out_oidx = b.j >= 0 ? b.oidx : kNoIdx;
+}
+
+#else
+// Warp-synchronous search: every lane of every warp calls this once per tile (it contains warp
+// collectives, no block barrier).  `active` lanes carry a query s (in the grid's frame); seed_j is the
+// sorted position of the neighbour found for this query last time (-1: none); delta >= 0 asks for a
+// motion budget (see header).  budget_out = certified budget (0 when none could be certified).
+template <bool EXACT, class SM>
+__device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool active, double sx,
+                                               double sy, double sz, double maxdist2, int seed_j,
+                                               float delta, int& out_j, double& out_d2,
+                                               unsigned& out_oidx, float& budget_out,
+                                               unsigned& stage2_count, bool /*dense*/ = false) {
   const int lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
   Best b;
@@ -570,5 +836,7 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SearchSmem& sm,
   out_d2 = b.d2;
   out_oidx = b.j >= 0 ? b.oidx : kNoIdx;
 }
+
+#endif
 
 }  // namespace b200

@@ -282,7 +282,12 @@ icp_search_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
     double bd2;
     unsigned boidx;
     float newbud;
-    nn_warp_search<EXACT>(model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2);
+    // queue entries are in the data scan's cell order: a full batch with a short index span is "dense"
+    const unsigned imax = __reduce_max_sync(0xffffffffu, on ? i : 0u);
+    const unsigned imin = __reduce_min_sync(0xffffffffu, on ? i : 0xffffffffu);
+    const bool dense = __all_sync(0xffffffffu, on) && imax - imin <= (unsigned)kTileSpan;
+    nn_warp_search<EXACT>(model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2,
+                          dense);
     if (on) {
       nn_cache[i] = bj;
       nn_budget[i] = newbud;

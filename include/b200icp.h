@@ -193,6 +193,34 @@ int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve
 int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
                      double max_dist_match2, double C[36], double CD[6], uint64_t* npairs);
 
+/* ---- LUM / graph back-end ----------------------------------------------------------------
+ * Host-side loop around b200icp_lum_link; scans keep their pose in transMat / dalignxf, points are never moved.
+ *   b200icp_graph_from_poses  Graph::Graph(int nodes, double cldist2, int loopsize) (src/slam6d/graph.cc:108-127):
+ *                             chain links (i, i+1) plus (j, k) for k - j > loopsize and |rPos_j - rPos_k|^2 <
+ *                             cldist2.  links = [2 * cap] ints (from, to); *n_links = links needed (EINVAL when
+ *                             it exceeds cap; pass links = NULL to count only).
+ *   b200icp_lum_fill_gb       lum6DEuler::FillGB3D (src/slam6d/lum6Deuler.cc:265-304) for the given links: ADDS the
+ *                             link blocks into dense row-major G [(6(n-1))^2] and B [6(n-1)] (scan 0 is fixed).
+ *                             A link-sharded caller fills its own links and all-reduces [G|B] (parallel.py).
+ *   b200icp_lum_solve_update  the rest of one doGraphSlam6D iteration (lum6Deuler.cc:377-470): X = G^-1 B by dense
+ *                             Cholesky (graphSlam6D::solveCholesky, graphSlam6D.cc:245-293; the reference's default
+ *                             cs_cholsol solves the same system), pose correction Ha^-1 X_i per scan and
+ *                             Scan::transformToEuler (scan.cc:1061-1083) on transMat / dalignxf.
+ *                             ESTATE when G is not positive definite.
+ *   b200icp_lum_graph_slam    lum6DEuler::doGraphSlam6D (lum6Deuler.cc:314-479): iterates the two steps until
+ *                             nr_it or sum_position_diff / n_scans <= epsilon_lum; *ret_out = that quotient.
+ *   b200icp_matrix4_to_euler  Matrix4ToEuler (include/slam6d/globals.icc:540-578). */
+int b200icp_graph_from_poses(const double* rpos, int n_scans, double cldist2, int loopsize, int* links,
+                             int cap, int* n_links);
+int b200icp_lum_fill_gb(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
+                        int n_links, double max_dist_match2, double* G, double* B, uint64_t* npairs_out);
+int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const double* G, const double* B,
+                             double* sum_position_diff);
+int b200icp_lum_graph_slam(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
+                           int n_links, double max_dist_match2, int nr_it, double epsilon_lum,
+                           double* ret_out, int* iterations_out);
+void b200icp_matrix4_to_euler(const double m[16], double rPosTheta[3], double rPos[3]);
+
 /* ---- normals --------------------------------------------------------------------------------
  * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):
  * exact k nearest neighbours (the point itself included), PCA, smallest-eigenvalue eigenvector,

@@ -867,3 +867,132 @@ extern "C" long orc_lum_link(void* model_tree, const double* model_dalignxf, con
   for (int i = 0; i < 6; ++i) { CD[i] = MZ[i] * ss; for (int k = 0; k < 6; ++k) C[6 * i + k] = MM[i][k] * ss; }
   return m;
 }
+
+// ---- Graph / doGraphSlam6D (TEST INFRASTRUCTURE, like everything in this file) ------------------------------
+// Graph::Graph(int nodes, double cldist2, int loopsize), graph.cc:108-127
+extern "C" int orc_graph_from_poses(const double* rpos, int n, double cldist2, int loopsize, int* links, int cap) {
+  int m = 0;
+  for (int i = 0; i + 1 < n; ++i) { if (m < cap) { links[2 * m] = i; links[2 * m + 1] = i + 1; } ++m; }
+  for (int j = 0; j < n; ++j)
+    for (int k = j + 1; k < n; ++k) {
+      double d2 = sq(rpos[3 * j] - rpos[3 * k]) + sq(rpos[3 * j + 1] - rpos[3 * k + 1]) + sq(rpos[3 * j + 2] - rpos[3 * k + 2]);
+      if (abs(k - j) > loopsize && d2 < cldist2) { if (m < cap) { links[2 * m] = j; links[2 * m + 1] = k; } ++m; }
+    }
+  return m;
+}
+
+// Matrix4ToEuler, globals.icc:540-578
+extern "C" void orc_matrix4_to_euler(const double* a, double* th, double* pos) {
+  th[1] = a[0] > 0.0 ? asin(a[8]) : M_PI - asin(a[8]);
+  double C = cos(th[1]);
+  if (fabs(C) > 0.005) { th[0] = atan2(-a[9] / C, a[10] / C); th[2] = atan2(-a[4] / C, a[0] / C); }
+  else { th[0] = 0.0; th[2] = atan2(a[1], a[5]); }
+  if (pos) { pos[0] = a[12]; pos[1] = a[13]; pos[2] = a[14]; }
+}
+
+// general dense solve by LU with partial pivoting (deliberately NOT the Cholesky route the product takes:
+// G is SPD, both must give the same X up to rounding)
+static bool lu_solve(int n, std::vector<double>& A, std::vector<double>& b) {
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r) if (fabs(A[(size_t)r * n + c]) > fabs(A[(size_t)piv * n + c])) piv = r;
+    if (A[(size_t)piv * n + c] == 0.0) return false;
+    if (piv != c) { for (int k = 0; k < n; ++k) std::swap(A[(size_t)c * n + k], A[(size_t)piv * n + k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < n; ++r) {
+      double f = A[(size_t)r * n + c] / A[(size_t)c * n + c];
+      if (f == 0.0) continue;
+      for (int k = c; k < n; ++k) A[(size_t)r * n + k] -= f * A[(size_t)c * n + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; --r) {
+    double t = b[r];
+    for (int k = r + 1; k < n; ++k) t -= A[(size_t)r * n + k] * b[k];
+    b[r] = t / A[(size_t)r * n + r];
+  }
+  return true;
+}
+
+// lum6DEuler::doGraphSlam6D (lum6Deuler.cc:314-479) with FillGB3D (:265-304) and Scan::transformToEuler
+// (scan.cc:1061-1083) over in-memory scans.  xyz_all: the scans' "xyz reduced original" rows back to back
+// (offsets[n+1]); transmats / dalignxfs: 16 doubles per scan, in/out.  Like the reference, the "xyz reduced"
+// working copy of every scan is MOVED by each transform (the product never moves points).
+// PARITY NOTE: lum6Deuler.cc does not compile here (CXSparse); the linear solve is the reference's SPD system
+// solved densely.  G_out/B_out (optional) return the system of the first iteration.
+extern "C" int orc_lum_graph_slam(int n_scans, const double* xyz_all, const long* offsets, const int* links,
+                                  int n_links, double maxdist2, int nr_it, double eps, double* transmats,
+                                  double* dalignxfs, double* ret_out, double* G_out, double* B_out) {
+  if (n_scans <= 0) return -1;
+  std::vector<void*> trees(n_scans);
+  std::vector<std::vector<double>> cur(n_scans);
+  for (int i = 0; i < n_scans; ++i) {
+    long n = offsets[i + 1] - offsets[i];
+    trees[i] = orc_tree_create(xyz_all + 3 * offsets[i], n, 20);
+    cur[i].assign(xyz_all + 3 * offsets[i], xyz_all + 3 * offsets[i + 1]);
+    for (long k = 0; k < n; ++k) xf_point_inplace(dalignxfs + 16 * i, &cur[i][3 * k]);
+  }
+  double ret = DBL_MAX;
+  int it = 0;
+  const int dim = 6 * (n_scans - 1);
+  for (; it < nr_it && ret > eps && dim > 0; ++it) {
+    std::vector<double> G((size_t)dim * dim, 0.0), B(dim, 0.0);
+    for (int l = 0; l < n_links; ++l) {
+      int first = links[2 * l], second = links[2 * l + 1], a = first - 1, b = second - 1;
+      double C[36], CD[6];
+      orc_lum_link(trees[first], dalignxfs + 16 * first, cur[second].data(), (long)(cur[second].size() / 3),
+                   maxdist2, C, CD);
+      for (int r = 0; r < 6; ++r) {
+        if (a >= 0) B[6 * a + r] += CD[r];
+        if (b >= 0) B[6 * b + r] -= CD[r];
+        for (int c = 0; c < 6; ++c) {
+          if (a >= 0) G[(size_t)(6 * a + r) * dim + 6 * a + c] += C[6 * r + c];
+          if (b >= 0) G[(size_t)(6 * b + r) * dim + 6 * b + c] += C[6 * r + c];
+          if (a >= 0 && b >= 0) {
+            G[(size_t)(6 * a + r) * dim + 6 * b + c] -= C[6 * r + c];
+            G[(size_t)(6 * b + r) * dim + 6 * a + c] -= C[6 * r + c];
+          }
+        }
+      }
+    }
+    if (it == 0 && G_out) memcpy(G_out, G.data(), G.size() * sizeof(double));
+    if (it == 0 && B_out) memcpy(B_out, B.data(), B.size() * sizeof(double));
+    std::vector<double> X = B, A = G;
+    if (!lu_solve(dim, A, X)) return -2;
+    double sum_position_diff = 0.0;
+    for (int i = 1; i < n_scans; ++i) {
+      double* T = transmats + 16 * i;
+      double* dal = dalignxfs + 16 * i;
+      double th[3], pos[3];
+      orc_matrix4_to_euler(T, th, pos);
+      double xa = pos[0], ya = pos[1], za = pos[2];
+      double ctx = cos(th[0]), stx = sin(th[0]), cty = cos(th[1]), sty = sin(th[1]);
+      double Ha[6][6] = {{0}};
+      for (int k = 0; k < 6; ++k) Ha[k][k] = 1.0;
+      Ha[0][4] = -za * ctx + ya * stx;       Ha[0][5] = ya * cty * ctx + za * stx * cty;
+      Ha[1][3] = za;  Ha[1][4] = -xa * stx;  Ha[1][5] = -xa * ctx * cty + za * sty;
+      Ha[2][3] = -ya; Ha[2][4] = xa * ctx;   Ha[2][5] = -xa * cty * stx - ya * sty;
+      Ha[3][5] = sty;
+      Ha[4][4] = stx; Ha[4][5] = ctx * cty;
+      Ha[5][4] = ctx; Ha[5][5] = -stx * cty;
+      double result[6];
+      for (int k = 0; k < 6; ++k) result[k] = X[6 * (i - 1) + k];
+      if (!solve6(Ha, result)) return -3;        // result = Ha^-1 * Xtmp
+      double npos[3], nth[3];
+      for (int k = 0; k < 3; ++k) { npos[k] = pos[k] - result[k]; nth[k] = th[k] - result[k + 3]; }
+      double tinv[16], alignxf[16], tmp[16];
+      mat_inv(T, tinv);
+      orc_euler_to_matrix4(npos, nth, alignxf);
+      const double* steps[2] = {tinv, alignxf};
+      for (int s = 0; s < 2; ++s) {            // Scan::transform twice: points, transMat, dalignxf
+        for (size_t k = 0; k < cur[i].size() / 3; ++k) xf_point_inplace(steps[s], &cur[i][3 * k]);
+        mat_mul(steps[s], T, tmp); memcpy(T, tmp, sizeof tmp);
+        mat_mul(steps[s], dal, tmp); memcpy(dal, tmp, sizeof tmp);
+      }
+      sum_position_diff += sqrt(sq(result[0]) + sq(result[1]) + sq(result[2]));
+    }
+    ret = sum_position_diff / (double)n_scans;
+  }
+  for (int i = 0; i < n_scans; ++i) orc_tree_free(trees[i]);
+  if (ret_out) *ret_out = ret;
+  return it;
+}

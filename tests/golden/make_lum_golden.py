@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Golden vectors for the LUM / graph back-end helpers, generated from the COMPILED REFERENCE
+(oracle/_ref/libref3dtk.so, built from /root/reference by oracle/Makefile).  Run in the build container:
+    python tests/golden/make_lum_golden.py      -> tests/golden/lum_vectors.npz
+Contents: Matrix4ToEuler (globals.icc:540-578) on poses covering both asin branches and the gimbal-lock branch.
+lum6Deuler.cc / graph.cc themselves do not compile here (CXSparse, boost::graph), so no reference outputs exist
+for doGraphSlam6D or Graph(): those are checked against oracle/oracle_icp.cpp only (parity unpinned there)."""
+import os, sys
+import numpy as np
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import orclib
+
+L = orclib.ref()
+assert L is not None, "build oracle/_ref first (make -C oracle ref)"
+L.ref_matrix4_to_euler.restype = None
+L.ref_matrix4_to_euler.argtypes = [orclib.vp, orclib.vp, orclib.vp]
+rng = np.random.default_rng(20261017)
+poses, mats, thetas, positions = [], [], [], []
+cases = [np.array([0.0, 0.0, 0.0]), np.array([0.3, -0.2, 0.1]), np.array([0.1, 2.5, -0.4]),      # cos(ty) < 0 branch
+         np.array([-1.2, -2.9, 3.0]), np.array([0.4, np.pi / 2, 0.2]), np.array([0.4, -np.pi / 2 + 1e-4, 1.0])]
+cases += [rng.uniform(-np.pi, np.pi, 3) for _ in range(58)]
+for th in cases:
+    pos = rng.uniform(-500, 500, 3)
+    M = np.zeros(16)
+    L.ref_euler_to_matrix4(orclib.P(pos), orclib.P(np.asarray(th, dtype=np.float64)), orclib.P(M))
+    out_th, out_pos = np.zeros(3), np.zeros(3)
+    L.ref_matrix4_to_euler(orclib.P(M), orclib.P(out_th), orclib.P(out_pos))
+    mats.append(M); thetas.append(out_th); positions.append(out_pos)
+np.savez_compressed(os.path.join(HERE, "lum_vectors.npz"), m4=np.array(mats), theta=np.array(thetas),
+                    pos=np.array(positions))
+print("wrote", len(mats), "Matrix4ToEuler vectors")

@@ -54,6 +54,10 @@ def port():
         L.orc_match.argtypes = [vp, vp, vp, vp, cl, vp, vp, ci, ci, cd, ci, cd, ci, vp, vp, vp]
         L.orc_normals_knn.restype = None; L.orc_normals_knn.argtypes = [vp, cl, ci, vp, vp]
         L.orc_lum_link.restype = cl; L.orc_lum_link.argtypes = [vp, vp, vp, cl, cd, vp, vp]
+        L.orc_graph_from_poses.restype = ci; L.orc_graph_from_poses.argtypes = [vp, ci, cd, ci, vp, ci]
+        L.orc_matrix4_to_euler.restype = None; L.orc_matrix4_to_euler.argtypes = [vp, vp, vp]
+        L.orc_lum_graph_slam.restype = ci
+        L.orc_lum_graph_slam.argtypes = [ci, vp, vp, vp, ci, cd, ci, cd, vp, vp, vp, vp, vp]
         _port = L
     return _port
 
@@ -167,6 +171,30 @@ def port_lum_link(model_xyz, data_xyz, maxdist2, model_dalignxf=None):
     Cm, CD = np.zeros(36), np.zeros(6)
     m = port().orc_lum_link(tree.h, P(S), P(d), len(d), maxdist2, P(Cm), P(CD))
     return Cm.reshape(6, 6), CD, m
+
+
+def port_graph_from_poses(rpos, cldist2, loopsize):
+    rpos = np.ascontiguousarray(rpos, dtype=np.float64)
+    cap = rpos.shape[0] * rpos.shape[0] + 1
+    links = np.zeros((cap, 2), dtype=np.int32)
+    m = port().orc_graph_from_poses(P(rpos), rpos.shape[0], cldist2, loopsize, links.ctypes.data, cap)
+    return links[:m].copy()
+
+
+def port_lum_graph_slam(scans_xyz, links, maxdist2, nr_it, eps, transmats, dalignxfs=None):
+    """orc_lum_graph_slam over in-memory scans -> dict(iterations, ret, transmats, dalignxfs, G, B)"""
+    n = len(scans_xyz)
+    xyz = np.ascontiguousarray(np.concatenate(scans_xyz, axis=0), dtype=np.float64)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for s in scans_xyz])
+    links = np.ascontiguousarray(links, dtype=np.int32)
+    T = np.ascontiguousarray(transmats, dtype=np.float64).reshape(n, 16).copy()
+    D = np.tile(identity(), (n, 1)) if dalignxfs is None else np.ascontiguousarray(dalignxfs, dtype=np.float64).reshape(n, 16).copy()
+    dim = 6 * (n - 1)
+    G, B, ret = np.zeros((dim, dim)), np.zeros(dim), np.zeros(1)
+    it = port().orc_lum_graph_slam(n, P(xyz), off.ctypes.data, links.ctypes.data, links.shape[0], maxdist2, nr_it, eps,
+                                   P(T), P(D), P(ret), P(G), P(B))
+    return {"iterations": it, "ret": float(ret[0]), "transmats": T, "dalignxfs": D, "G": G, "B": B}
 
 
 def octree_centres(pts, voxel):
