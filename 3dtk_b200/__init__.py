@@ -67,6 +67,9 @@ def _load():
                                          C.POINTER(C.c_uint64)]),
         "b200icp_scan_get_pose": (i32, [vp, dp, dp]),
         "b200icp_scan_set_pose": (i32, [vp, dp, dp]),
+        "b200icp_scan_transform": (i32, [vp, dp]),
+        "b200icp_metascan_create": (i32, [vp, dp, i32, f64, f64, C.POINTER(vp)]),
+        "b200icp_do_icp": (i32, [vp, dp, i32, C.POINTER(MatchParams), i32, i32, i32, dp, dp]),
         "b200icp_scan_download": (i32, [vp, vp, dp, dp]),
         "b200icp_find_closest": (i32, [vp, vp, dp, f64, C.POINTER(C.c_int64)]),
         "b200icp_nn_batch": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
@@ -254,6 +257,22 @@ class Scan:
         d = None if dalignxf is None else _f64(dalignxf).reshape(16)
         _check(lib.b200icp_scan_set_pose(self._h, _ptr(t), _ptr(d)))
 
+    def transform(self, alignxf):
+        """Scan::transform bookkeeping (scan.cc:851-898): pose matrices only, points stay where they are"""
+        a = _f64(alignxf).reshape(16)
+        _check(lib.b200icp_scan_transform(self._h, _ptr(a)))
+
+    @classmethod
+    def metascan(cls, ctx, scans, cell_edge=0.0, max_dist_hint=0.0):
+        """MetaScan(scans) (metaScan.cc:27-69): one search structure over the members' current positions"""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        h = C.c_void_p()
+        arr = (C.c_void_p * len(scans))(*[s._h for s in scans])
+        _check(lib.b200icp_metascan_create(ctx._h, arr, len(scans), cell_edge, max_dist_hint, C.byref(h)))
+        self._h = h
+        return self
+
     def download(self, with_normals=False):
         n = len(self)
         xyz = np.empty((n, 3))
@@ -327,6 +346,19 @@ class icp6D:
             prof = {"nn_ms": nn, "solve_ms": sv, "stage2": s2, "searches": se}
         return {"profile": prof, "iterations": res.iterations, "iterations_run": k, "rms": rms[:k].copy(),
                 "npairs": npairs[:k].copy(), "result": res}
+
+
+    def doICP(self, all_scans, pairing_mode=CLOSEST_POINT, extrapolate_pose=True, meta=False, max_num_metascans=0,
+              transmat_org=None):
+        """icp6D::doICP (icp6D.cc:374-437) -> iterations per scan.  Updates the scans' poses."""
+        p = self.params
+        p.pairing_mode = pairing_mode
+        arr = (C.c_void_p * len(all_scans))(*[s._h for s in all_scans])
+        org = None if transmat_org is None else _f64(transmat_org).reshape(-1)
+        its = np.zeros(max(len(all_scans), 1), dtype=np.int32)
+        _check(lib.b200icp_do_icp(self.ctx._h, arr, len(all_scans), C.byref(p), 1 if extrapolate_pose else 0,
+                                  1 if meta else 0, int(max_num_metascans), _ptr(org), _ptr(its)))
+        return its[:len(all_scans)]
 
 
 def lum_link(ctx, first, second, max_dist_match2):

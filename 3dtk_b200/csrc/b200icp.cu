@@ -566,6 +566,57 @@ int b200icp_scan_set_pose(b200icp_scan* scan, const double transMat[16], const d
   return B200ICP_OK;
 }
 
+int b200icp_scan_transform(b200icp_scan* scan, const double alignxf[16]) {
+  if (!scan || !alignxf) return fail(B200ICP_EINVAL, "scan_transform: NULL argument");
+  double tmp[16];
+  m4_mul(alignxf, scan->transMat, tmp);
+  memcpy(scan->transMat, tmp, sizeof tmp);
+  m4_mul(alignxf, scan->dalignxf, tmp);
+  memcpy(scan->dalignxf, tmp, sizeof tmp);
+  // transform3normal (globals.icc:1465-1475) multiplies by the transposed rotation block, as in solve_step_serial
+  double nn[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      nn[3 * r + c] = alignxf[4 * r + 0] * scan->nmat[c] + alignxf[4 * r + 1] * scan->nmat[3 + c] +
+                      alignxf[4 * r + 2] * scan->nmat[6 + c];
+  memcpy(scan->nmat, nn, sizeof nn);
+  return B200ICP_OK;
+}
+
+int b200icp_metascan_create(b200icp_ctx* ctx, const b200icp_scan* const* scans, int n_scans, double cell_edge,
+                            double max_dist_hint, b200icp_scan** out) {
+  if (!ctx || !scans || !out) return fail(B200ICP_EINVAL, "metascan_create: NULL argument");
+  *out = nullptr;
+  if (n_scans <= 0) return fail(B200ICP_EEMPTY, "metascan_create: no member scans");
+  size_t total = 0;
+  for (int i = 0; i < n_scans; ++i) {
+    if (!scans[i]) return fail(B200ICP_EINVAL, "metascan_create: NULL member scan");
+    total += scans[i]->n;
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> d_xyz, d_xf;
+  CU_TRY(d_xyz.alloc(3 * total));
+  CU_TRY(d_xf.alloc((size_t)25 * n_scans));
+  std::vector<double> hx((size_t)25 * n_scans);
+  for (int i = 0; i < n_scans; ++i) {
+    memcpy(&hx[(size_t)25 * i], scans[i]->dalignxf, 16 * sizeof(double));
+    memcpy(&hx[(size_t)25 * i + 16], scans[i]->nmat, 9 * sizeof(double));
+  }
+  CU_TRY(cudaMemcpyAsync(d_xf.p, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  size_t off = 0;
+  for (int i = 0; i < n_scans; ++i) {   // member i's current "xyz reduced", in its original row order
+    const b200icp_scan* s = scans[i];
+    scan_export_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(s->g.p64, nullptr, s->perm.p, (uint32_t)s->n,
+                                                                       d_xf.p + (size_t)25 * i, d_xyz.p + 3 * off,
+                                                                       nullptr);
+    off += s->n;
+  }
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(st));   // hx must outlive the copy
+  return b200icp_scan_create_device(ctx, d_xyz.p, nullptr, total, cell_edge, max_dist_hint, out);
+}
+
 int b200icp_scan_download(b200icp_ctx* ctx, const b200icp_scan* scan, double* xyz_out, double* nrm_out) {
   if (!ctx || !scan || !xyz_out) return fail(B200ICP_EINVAL, "scan_download: NULL argument");
   if (nrm_out && !scan->has_normals) return fail(B200ICP_ESTATE, "scan_download: scan has no normals");

@@ -80,6 +80,15 @@ int b200icp_scan_grid_info(const b200icp_scan* scan, int dims[3], double* cell_e
 /* Scan::transMat / Scan::dalignxf (scan.cc:878-898).  Either pointer may be NULL. */
 int b200icp_scan_get_pose(const b200icp_scan* scan, double transMat[16], double dalignxf[16]);
 int b200icp_scan_set_pose(b200icp_scan* scan, const double transMat[16], const double dalignxf[16]);
+/* Scan::transform's bookkeeping (scan.cc:851-898) without touching points: transMat <- alignxf*transMat,
+ * dalignxf <- alignxf*dalignxf, normal map by the transform3normal rule.  The kernels apply dalignxf on load. */
+int b200icp_scan_transform(b200icp_scan* scan, const double alignxf[16]);
+/* MetaScan + KDtreeMetaManaged (src/slam6d/metaScan.cc:27-69, kdMeta.cc:34-72): ONE search structure over the
+ * CURRENT positions ("xyz reduced") of all member scans, member after member in their original row order,
+ * with identity pose.  Built on the device (export of every member through its dalignxf, then the usual
+ * grid build); the members are not modified and may be destroyed afterwards. */
+int b200icp_metascan_create(b200icp_ctx* ctx, const b200icp_scan* const* scans, int n_scans, double cell_edge,
+                            double max_dist_hint, b200icp_scan** out);
 /* Current "xyz reduced" (= dalignxf * original) and "normal reduced", original row order;
  * what Scan::transformReduced (scan.cc:851-875) leaves in the arrays.  nrm_out may be NULL. */
 int b200icp_scan_download(b200icp_ctx* ctx, const b200icp_scan* scan, double* xyz_out,
@@ -157,6 +166,16 @@ typedef struct b200icp_match_result {
 int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* data,
                   const b200icp_match_params* params, double* rms_per_iter,
                   uint64_t* npairs_per_iter, b200icp_match_result* result);
+
+/* ---- icp6D::doICP (src/slam6d/icp6D.cc:374-437): sequential matching of a scan sequence --------------------
+ * For i = 1..n-1: optional odometry extrapolation (Scan::mergeCoordinatesWithRoboterPosition, scan.cc:826-833:
+ * scan i is moved by transMat_{i-1} * inv(transMatOrg_{i-1})), then match(previous or metascan, current).
+ * transMatOrg = 16 doubles per scan: the pose each scan was loaded with (NULL: the transMat at entry).
+ * meta != 0 matches against a metascan of all scans processed so far (the last max_num_metascans when > 0),
+ * rebuilt after every scan like the reference.  iterations_out (may be NULL) receives n entries (entry 0 = 0). */
+int b200icp_do_icp(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const b200icp_match_params* params,
+                   int extrapolate_pose, int meta, int max_num_metascans, const double* transMatOrg,
+                   int* iterations_out);
 
 /* ---- query-sharded match across GPUs (the reference's pICP split, scan.cc:1335-1342) --------
  * Every rank holds the whole model scan and a contiguous slice of the data scan.  The per-iteration sum of the

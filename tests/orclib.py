@@ -173,6 +173,52 @@ def port_lum_link(model_xyz, data_xyz, maxdist2, model_dalignxf=None):
     return Cm.reshape(6, 6), CD, m
 
 
+def do_icp(match_fn, scans_xyz, transmats_org, extrapolate_pose=True, meta=False, max_num_metascans=0, **kw):
+    """icp6D::doICP (icp6D.cc:374-437) over in-memory scans, every match done by `match_fn` (port_match or
+    ref_match -- the compiled reference).  scans_xyz: points in the global frame at load ("xyz reduced original");
+    transmats_org: the poses they were loaded with.  Returns dict(transmats, dalignxfs, iterations, xyz)."""
+    L = port()
+    n = len(scans_xyz)
+    org = [np.ascontiguousarray(t, dtype=np.float64).reshape(16) for t in transmats_org]
+    cur = [np.ascontiguousarray(s, dtype=np.float64).copy() for s in scans_xyz]
+    T = [t.copy() for t in org]
+    D = [identity() for _ in range(n)]
+    its = [0] * n
+
+    def apply(M, i):          # Scan::transform: points, transMat, dalignxf
+        R = M.reshape(4, 4).T
+        cur[i] = cur[i] @ R[:3, :3].T + R[:3, 3]
+        for arr in (T, D):
+            out = np.zeros(16)
+            L.orc_mmult(P(M), P(arr[i]), P(out))
+            arr[i] = out
+
+    meta_list = []
+    for i in range(n):
+        if i > 0:
+            if extrapolate_pose:   # Scan::mergeCoordinatesWithRoboterPosition, scan.cc:826-833
+                inv, delta = np.zeros(16), np.zeros(16)
+                L.orc_m4inv(P(org[i - 1]), P(inv))
+                L.orc_mmult(P(T[i - 1]), P(inv), P(delta))
+                apply(delta, i)
+            if meta:
+                model, mdal = np.concatenate([cur[j] for j in meta_list], axis=0), identity()
+            else:
+                model, mdal = scans_xyz[i - 1], D[i - 1]
+            r = match_fn(model, cur[i], model_dalignxf=mdal, **kw)
+            its[i] = r["iterations"]
+            cur[i] = r["xyz"]
+            for arr in (T, D):
+                out = np.zeros(16)
+                L.orc_mmult(P(r["transmat"]), P(arr[i]), P(out))
+                arr[i] = out
+        if meta and i != n - 1:
+            meta_list.append(i)
+            if max_num_metascans > 0:
+                meta_list = meta_list[-max_num_metascans:]
+    return {"transmats": np.array(T), "dalignxfs": np.array(D), "iterations": its, "xyz": cur}
+
+
 def port_graph_from_poses(rpos, cldist2, loopsize):
     rpos = np.ascontiguousarray(rpos, dtype=np.float64)
     cap = rpos.shape[0] * rpos.shape[0] + 1
