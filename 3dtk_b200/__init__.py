@@ -69,7 +69,18 @@ def _load():
         "b200icp_scan_set_pose": (i32, [vp, dp, dp]),
         "b200icp_scan_transform": (i32, [vp, dp]),
         "b200icp_metascan_create": (i32, [vp, dp, i32, f64, f64, C.POINTER(vp)]),
-        "b200icp_do_icp": (i32, [vp, dp, i32, C.POINTER(MatchParams), i32, i32, i32, dp, dp]),
+        "b200icp_do_icp": (i32, [vp, dp, i32, C.POINTER(MatchParams), i32, i32, i32, dp, dp, vp]),
+        "b200icp_last_poses": (i32, [vp, i32, dp]),
+        "b200icp_read_uos": (i32, [C.c_char_p, C.POINTER(vp), C.POINTER(sz)]),
+        "b200icp_read_pose": (i32, [C.c_char_p, dp, dp]),
+        "b200icp_free": (None, [vp]),
+        "b200icp_frames_create": (vp, [i32]),
+        "b200icp_frames_destroy": (None, [vp]),
+        "b200icp_frames_add": (i32, [vp, i32, dp, i32]),
+        "b200icp_frames_transform": (i32, [vp, i32, dp, i32, i32]),
+        "b200icp_frames_count": (i32, [vp, i32]),
+        "b200icp_frames_get": (i32, [vp, i32, i32, dp, C.POINTER(i32)]),
+        "b200icp_frames_save": (i32, [vp, i32, C.c_char_p, i32]),
         "b200icp_scan_download": (i32, [vp, vp, dp, dp]),
         "b200icp_find_closest": (i32, [vp, vp, dp, f64, C.POINTER(C.c_int64)]),
         "b200icp_nn_batch": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
@@ -85,8 +96,8 @@ def _load():
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
         "b200icp_graph_from_poses": (i32, [dp, i32, f64, i32, dp, i32, C.POINTER(i32)]),
         "b200icp_lum_fill_gb": (i32, [vp, dp, i32, dp, i32, f64, dp, dp, dp]),
-        "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64)]),
-        "b200icp_lum_graph_slam": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, C.POINTER(f64), C.POINTER(i32)]),
+        "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64), vp]),
+        "b200icp_lum_graph_slam": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, C.POINTER(f64), C.POINTER(i32), vp]),
         "b200icp_matrix4_to_euler": (None, [dp, dp, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_reduce_octree_center": (i32, [vp, dp, sz, f64, dp, C.POINTER(sz)]),
@@ -348,8 +359,15 @@ class icp6D:
                 "npairs": npairs[:k].copy(), "result": res}
 
 
+    def last_poses(self):
+        """transMat of the data scan after every iteration of the last match (what Scan::transform saw)"""
+        n = lib.b200icp_last_poses(self.ctx._h, 0, None)
+        out = np.zeros((max(n, 1), 16))
+        lib.b200icp_last_poses(self.ctx._h, n, _ptr(out))
+        return out[:n]
+
     def doICP(self, all_scans, pairing_mode=CLOSEST_POINT, extrapolate_pose=True, meta=False, max_num_metascans=0,
-              transmat_org=None):
+              transmat_org=None, frames=None):
         """icp6D::doICP (icp6D.cc:374-437) -> iterations per scan.  Updates the scans' poses."""
         p = self.params
         p.pairing_mode = pairing_mode
@@ -357,7 +375,8 @@ class icp6D:
         org = None if transmat_org is None else _f64(transmat_org).reshape(-1)
         its = np.zeros(max(len(all_scans), 1), dtype=np.int32)
         _check(lib.b200icp_do_icp(self.ctx._h, arr, len(all_scans), C.byref(p), 1 if extrapolate_pose else 0,
-                                  1 if meta else 0, int(max_num_metascans), _ptr(org), _ptr(its)))
+                                  1 if meta else 0, int(max_num_metascans), _ptr(org), _ptr(its),
+                                  frames._h if frames is not None else None))
         return its[:len(all_scans)]
 
 
@@ -366,6 +385,61 @@ def lum_link(ctx, first, second, max_dist_match2):
     Cm, CD, n = np.zeros(36), np.zeros(6), C.c_uint64(0)
     _check(lib.b200icp_lum_link(ctx._h, first._h, second._h, max_dist_match2, _ptr(Cm), _ptr(CD), C.byref(n)))
     return Cm.reshape(6, 6), CD, n.value
+
+
+FRAME_INVALID, FRAME_ICP, FRAME_ICPINACTIVE, FRAME_LUM, FRAME_ELCH = 0, 1, 2, 3, 4   # Scan::AlgoType
+
+
+def read_uos(path):
+    """ScanIO_uos point file -> (n, 3) float64"""
+    p, n = C.c_void_p(), C.c_size_t(0)
+    _check(lib.b200icp_read_uos(os.fsencode(path), C.byref(p), C.byref(n)))
+    try:
+        out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(max(n.value, 1) * 3,))[:3 * n.value]
+        return out.reshape(-1, 3).copy()
+    finally:
+        lib.b200icp_free(p)
+
+
+def read_pose(path):
+    """scanNNN.pose -> (rPos[3], rPosTheta[3] in radians)"""
+    pos, th = np.zeros(3), np.zeros(3)
+    _check(lib.b200icp_read_pose(os.fsencode(path), _ptr(pos), _ptr(th)))
+    return pos, th
+
+
+class Frames:
+    """The m_frames lists of a set of scans (BasicScan::addFrame / saveFrames, basicScan.cc:902-936)."""
+
+    def __init__(self, n_scans):
+        self._h = C.c_void_p(lib.b200icp_frames_create(n_scans))
+        self.n_scans = n_scans
+
+    def add(self, scan, transmat, type_):
+        t = _f64(transmat).reshape(16)
+        _check(lib.b200icp_frames_add(self._h, scan, _ptr(t), type_))
+
+    def transform(self, scan, transmats, type_, islum):
+        t = _f64(transmats).reshape(-1)
+        _check(lib.b200icp_frames_transform(self._h, scan, _ptr(t), type_, islum))
+
+    def get(self, scan):
+        """-> list of (transMat[16], type)"""
+        out = []
+        for k in range(lib.b200icp_frames_count(self._h, scan)):
+            m, t = np.zeros(16), C.c_int(0)
+            _check(lib.b200icp_frames_get(self._h, scan, k, _ptr(m), C.byref(t)))
+            out.append((m, t.value))
+        return out
+
+    def save(self, scan, path, append=False):
+        _check(lib.b200icp_frames_save(self._h, scan, os.fsencode(path), 1 if append else 0))
+
+    def __del__(self):
+        try:
+            lib.b200icp_frames_destroy(self._h)
+        except Exception:
+            pass
 
 
 def matrix4_to_euler(m):
@@ -423,20 +497,21 @@ class lum6DEuler:
         return G, B, npairs[:links.shape[0]]
 
     @staticmethod
-    def solve_update(scans, G, B):
+    def solve_update(scans, G, B, frames=None):
         """X = G^-1 B, pose corrections, Scan::transformToEuler -> sum of position differences"""
         s = C.c_double(0.0)
         G, B = _f64(G), _f64(B)
-        _check(lib.b200icp_lum_solve_update(_scan_array(scans), len(scans), _ptr(G), _ptr(B), C.byref(s)))
+        _check(lib.b200icp_lum_solve_update(_scan_array(scans), len(scans), _ptr(G), _ptr(B), C.byref(s),
+                                            frames._h if frames is not None else None))
         return s.value
 
-    def doGraphSlam6D(self, graph, scans, nr_it):
+    def doGraphSlam6D(self, graph, scans, nr_it, frames=None):
         """lum6DEuler::doGraphSlam6D -> (ret, iterations run)"""
         ret, it = C.c_double(0.0), C.c_int(0)
         links = np.ascontiguousarray(graph.links, dtype=np.int32)
         _check(lib.b200icp_lum_graph_slam(self.ctx._h, _scan_array(scans), len(scans), _ptr(links), links.shape[0],
                                           self.max_dist_match2_lum, int(nr_it), self.epsilon_lum, C.byref(ret),
-                                          C.byref(it)))
+                                          C.byref(it), frames._h if frames is not None else None))
         return ret.value, it.value
 
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libb200icp.so")
 
-SOURCES = ["b200icp.cu", "host_util.cpp", "lum_graph.cpp", "do_icp.cpp"]
+SOURCES = ["b200icp.cu", "host_util.cpp", "lum_graph.cpp", "do_icp.cpp", "scan_files.cpp"]
 HEADERS = ["common.cuh", "grid_build.cuh", "nn_search.cuh", "icp_kernels.cuh", "stream_kernels.cuh", "normals.cuh", "reduce.cuh", "solve.h",
            os.path.join("..", "..", "include", "b200icp.h")]
 

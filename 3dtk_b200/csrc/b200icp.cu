@@ -97,6 +97,8 @@ struct b200icp_ctx {
   DevBuf<IterState> d_state;
   IterState* h_state = nullptr;     // pinned, 2 slots (speculative chunk polling)
   DevBuf<double> rms_log;
+  DevBuf<double> pose_log;          // [max_iter][16], see IterState::pose_log
+  int pose_log_count = 0;           // iterations of the last match
   DevBuf<unsigned long long> npairs_log;
   DevBuf<unsigned> stage2_counter;
   DevBuf<unsigned> stage2_log;
@@ -333,6 +335,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
   ctx->partials.release();
   ctx->d_state.release();
   ctx->rms_log.release();
+  ctx->pose_log.release();
   ctx->npairs_log.release();
   ctx->stage2_counter.release();
   ctx->stage2_log.release();
@@ -757,6 +760,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
     return B200ICP_OK;
   }
   CU_TRY(ctx->rms_log.ensure((size_t)max_iter));
+  CU_TRY(ctx->pose_log.ensure(16 * (size_t)max_iter));
+  ctx->pose_log_count = 0;
   CU_TRY(ctx->npairs_log.ensure((size_t)max_iter));
   CU_TRY(ctx->stage2_log.ensure(2 * (size_t)max_iter));
   CU_TRY(ctx->nn_cache.ensure(data->n));
@@ -788,6 +793,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   hs->algo = algo;
   hs->napx_weighted = prm->napx_weighted;
   hs->max_iter = max_iter;
+  hs->pose_log = ctx->pose_log.p;
   CU_TRY(cudaMemcpyAsync(ctx->d_state.p, hs, sizeof(IterState), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(ctx->nn_cache.p, 0xFF, data->n * sizeof(int), st));  // -1: no cached neighbour
   CU_TRY(cudaMemsetAsync(ctx->nn_budget.p, 0, data->n * sizeof(float), st));
@@ -855,6 +861,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
     return fail(B200ICP_ECUDA, "match: sharded match timed out waiting for a peer's moments");
   res.iterations = fin.done ? fin.ret_iter : max_iter;
   res.iterations_run = fin.iters_run;
+  ctx->pose_log_count = fin.iters_run;
   res.kernel_launches = launches;
   res.stage2_queries_last = fin.stage2_last;
   if (fin.iters_run > 0) {
@@ -914,6 +921,17 @@ int b200icp_debug_timing(unsigned long long* out32) {
   return cudaMemcpyFromSymbol(out32, g_tl, 32 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+int b200icp_last_poses(b200icp_ctx* ctx, int cap, double* transmats) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  const int n = ctx->pose_log_count;
+  const int m = std::min(n, cap);
+  if (m > 0 && transmats) {
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMemcpy(transmats, ctx->pose_log.p, 16 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return n;
+}
 
 int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve_ms, uint32_t* stage2,
                          uint32_t* searches) {

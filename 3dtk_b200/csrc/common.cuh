@@ -52,6 +52,8 @@ struct IterState {
   int napx_weighted;
   int max_iter;
   unsigned int stage2_last;
+  double* pose_log;   // [max_iter][16] transMat after every iteration that produced a transform (frames, see
+                      // b200icp_last_poses); may be NULL
 };
 
 // Peer mailboxes of a query-sharded match.  Every rank owns one mailbox in its HBM, mapped into

@@ -135,6 +135,8 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
   for (int i = 0; i < 16; ++i) { st->Xprev[i] = st->X[i]; st->X[i] = tmp[i]; }
   m4_mul(alignxf, st->T, tmp);
   for (int i = 0; i < 16; ++i) st->T[i] = tmp[i];
+  if (st->pose_log)
+    for (int i = 0; i < 16; ++i) st->pose_log[16 * (st->iters_run - 1) + i] = tmp[i];
   // transform3normal (globals.icc:1465-1475) multiplies by the transposed rotation block:
   // Nm <- R^T Nm, R(r,c) = alignxf[4c+r]
   double nn[9];

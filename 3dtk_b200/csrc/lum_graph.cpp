@@ -156,7 +156,7 @@ int b200icp_lum_fill_gb(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scan
 }
 
 int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const double* G, const double* B,
-                             double* sum_position_diff) {
+                             double* sum_position_diff, b200icp_frames* frames) {
   if (!scans || !G || !B || n_scans < 2) return b200icp_set_error_(B200ICP_EINVAL, "lum_solve_update: bad argument");
   const int dim = 6 * (n_scans - 1);
   std::vector<double> A(G, G + (size_t)dim * dim), X(dim);
@@ -204,6 +204,11 @@ int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const doub
     b200icp_mmult(alignxf, t1, t2);
     memcpy(dal, t2, sizeof dal);
     b200icp_scan_set_pose(scans[i], T, dal);
+    if (frames) {   // transformToEuler(.., Scan::LUM, i != last ? 1 : 2), lum6Deuler.cc:447-451
+      std::vector<double> all((size_t)16 * n_scans);
+      for (int k = 0; k < n_scans; ++k) b200icp_scan_get_pose(scans[k], &all[(size_t)16 * k], nullptr);
+      b200icp_frames_transform(frames, i, all.data(), B200ICP_FRAME_LUM, i != n_scans - 1 ? 1 : 2);
+    }
     sum += sqrt(result[0] * result[0] + result[1] * result[1] + result[2] * result[2]);
   }
   if (sum_position_diff) *sum_position_diff = sum;
@@ -212,7 +217,7 @@ int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const doub
 
 int b200icp_lum_graph_slam(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
                            int n_links, double max_dist_match2, int nr_it, double epsilon_lum,
-                           double* ret_out, int* iterations_out) {
+                           double* ret_out, int* iterations_out, b200icp_frames* frames) {
   if (!ctx || !scans || !links) return b200icp_set_error_(B200ICP_EINVAL, "lum_graph_slam: NULL argument");
   if (n_scans <= 0) return b200icp_set_error_(B200ICP_EINVAL, "Zero scans in graph");   // lum6Deuler.cc:316-318
   double ret = DBL_MAX;
@@ -226,7 +231,7 @@ int b200icp_lum_graph_slam(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_s
       int rc = b200icp_lum_fill_gb(ctx, scans, n_scans, links, n_links, max_dist_match2, G.data(), B.data(), nullptr);
       if (rc != B200ICP_OK) return rc;
       double sum = 0.0;
-      rc = b200icp_lum_solve_update(scans, n_scans, G.data(), B.data(), &sum);
+      rc = b200icp_lum_solve_update(scans, n_scans, G.data(), B.data(), &sum, frames);
       if (rc != B200ICP_OK) return rc;
       ret = sum / (double)n_scans;
     }

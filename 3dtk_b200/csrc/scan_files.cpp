@@ -1,0 +1,267 @@
+// scan_files.cpp -- the wire formats on either side of the path, host only:
+//   uos point files    ScanIO_uos -> readASCII / handle_line (reference src/scanio/helper.cc:577-835): one point
+//                      per line, three blank-separated values, '#' comments, up to 10 unparsable lines tolerated
+//                      at the top of the file, \n or \r\n
+//   .pose files        six values, position then Euler angles in DEGREES (src/scanio/helper.cc:228-232)
+//   .frames files      BasicScan::saveFrames (src/slam6d/basicScan.cc:902-917): per frame 16 doubles written with
+//                      the default ostream format, each followed by a blank, then the AlgoType integer
+//                      (operator<< include/slam6d/globals.icc:123-132; enum include/slam6d/scan.h:126)
+// plus the frame bookkeeping of Scan::transform (src/slam6d/scan.cc:941-1000) that decides which scans receive a
+// frame of which type.  The reader parses the file in parallel chunks (std::from_chars), because text parsing is
+// what remains on the host once the correspondence search is gone.
+#include "../../include/b200icp.h"
+
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+extern "C" int b200icp_set_error_(int code, const char* msg);
+
+namespace {
+
+inline bool is_blank(char c) { return c == ' ' || c == '\t'; }
+
+// strtod semantics on one whole token (reference: strtoval -> strtod with an end-of-token check)
+bool parse_token(const char* b, const char* e, double* out) {
+  if (b == e) return false;
+  const char* p = b;
+  if (*p == '+') ++p;
+  auto r = std::from_chars(p, e, *out);
+  if (r.ec == std::errc() && r.ptr == e) return true;
+  std::string tmp(b, e);       // rare spellings from_chars does not take (hex floats, "infinity", locale free)
+  char* end = nullptr;
+  const double v = strtod(tmp.c_str(), &end);
+  if (end != tmp.c_str() + tmp.size()) return false;
+  *out = v;
+  return true;
+}
+
+// one line of a uos file: 0 = no point (empty / comment), 1 = point stored in v, -1 = parse error
+int parse_line(const char* b, const char* e, double v[3]) {
+  if (e > b && e[-1] == '\r') --e;
+  while (b < e && is_blank(*b)) ++b;
+  if (b == e || *b == '#') return 0;
+  int nv = 0;
+  const char* p = b;
+  while (p < e && *p != '#') {
+    const char* t = p;
+    while (t < e && !is_blank(*t) && *t != '#') ++t;
+    if (nv == 3) return -1;                       // "too many values in line"
+    if (!parse_token(p, t, &v[nv])) return -1;
+    ++nv;
+    p = t;
+    while (p < e && is_blank(*p)) ++p;
+  }
+  return nv == 3 ? 1 : -1;                         // "less values than in spec"
+}
+
+struct Frame { double m[16]; int type; };
+
+}  // namespace
+
+struct b200icp_frames {
+  std::vector<std::vector<Frame>> scans;
+};
+
+extern "C" {
+
+void b200icp_free(void* p) { free(p); }
+
+int b200icp_read_uos(const char* path, double** xyz_out, size_t* n_out) {
+  if (!path || !xyz_out || !n_out) return b200icp_set_error_(B200ICP_EINVAL, "read_uos: NULL argument");
+  *xyz_out = nullptr;
+  *n_out = 0;
+  FILE* f = fopen(path, "rb");
+  if (!f) return b200icp_set_error_(B200ICP_EINVAL, (std::string("read_uos: cannot open ") + path).c_str());
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> buf((size_t)(sz > 0 ? sz : 0));
+  if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) {
+    fclose(f);
+    return b200icp_set_error_(B200ICP_EINVAL, "read_uos: short read");
+  }
+  fclose(f);
+  const char* base = buf.data();
+  const char* end = base + buf.size();
+  // chunk boundaries on line starts
+  unsigned nthr = std::thread::hardware_concurrency();
+  if (nthr == 0) nthr = 1;
+  if (nthr > 32) nthr = 32;
+  if (buf.size() < (1u << 20)) nthr = 1;
+  std::vector<const char*> cut(nthr + 1);
+  cut[0] = base;
+  cut[nthr] = end;
+  for (unsigned t = 1; t < nthr; ++t) {
+    const char* p = base + buf.size() / nthr * t;
+    while (p < end && *p != '\n') ++p;
+    cut[t] = p < end ? p + 1 : end;
+    if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  }
+  struct Part { std::vector<double> xyz; std::vector<std::pair<size_t, signed char>> events; size_t lines = 0; };
+  // events: (line index inside the chunk, status) for every line that is not a plain point -- errors (-1) and
+  // point-free lines (0); the header rule needs their order relative to the points
+  std::vector<Part> parts(nthr);
+  auto work = [&](unsigned t) {
+    Part& P = parts[t];
+    const char* p = cut[t];
+    const char* e = cut[t + 1];
+    P.xyz.reserve((size_t)(e - p) / 24 * 3);
+    size_t line = 0;
+    while (p < e) {
+      const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+      const char* le = q ? q : e;
+      double v[3];
+      const int s = parse_line(p, le, v);
+      if (s == 1) {
+        if (P.xyz.empty()) P.events.push_back({line, 1});   // remember where the chunk's first point is
+        P.xyz.insert(P.xyz.end(), v, v + 3);
+      } else {
+        P.events.push_back({line, (signed char)s});
+      }
+      ++line;
+      p = q ? q + 1 : e;
+    }
+    P.lines = line;
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nthr; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  // header rule of readASCII (helper.cc:752-822): unparsable lines are skipped while no line has been read
+  // successfully yet (at most 10 of them); a successfully handled line -- a point, an empty line or a comment --
+  // ends the header, after which any unparsable line is fatal
+  int header = 10;
+  size_t line_base = 0;
+  for (unsigned t = 0; t < nthr; ++t) {
+    for (auto& ev : parts[t].events) {
+      if (ev.second == -1) {
+        header -= 1;
+        if (header < 0) {
+          std::ostringstream m;
+          m << "read_uos: unable to parse line " << (line_base + ev.first + 1) << " of " << path;
+          return b200icp_set_error_(B200ICP_EINVAL, m.str().c_str());
+        }
+      } else if (header >= 0) {
+        header = -1;
+      }
+    }
+    line_base += parts[t].lines;
+  }
+  size_t total = 0;
+  for (auto& P : parts) total += P.xyz.size();
+  double* out = (double*)malloc((total ? total : 1) * sizeof(double));
+  if (!out) return b200icp_set_error_(B200ICP_ENOMEM, "read_uos: out of memory");
+  size_t off = 0;
+  for (auto& P : parts) {
+    if (!P.xyz.empty()) memcpy(out + off, P.xyz.data(), P.xyz.size() * sizeof(double));
+    off += P.xyz.size();
+  }
+  *xyz_out = out;
+  *n_out = total / 3;
+  return B200ICP_OK;
+}
+
+int b200icp_read_pose(const char* path, double rPos[3], double rPosTheta[3]) {
+  if (!path || !rPos || !rPosTheta) return b200icp_set_error_(B200ICP_EINVAL, "read_pose: NULL argument");
+  std::ifstream f(path);
+  if (!f) return b200icp_set_error_(B200ICP_EINVAL, (std::string("read_pose: cannot open ") + path).c_str());
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 6; ++i) f >> v[i];                 // "read 6 plain doubles"
+  for (int i = 0; i < 3; ++i) {
+    rPos[i] = v[i];
+    rPosTheta[i] = v[i + 3] * M_PI / 180.0;              // rad(), globals.icc:172-175
+  }
+  return B200ICP_OK;
+}
+
+b200icp_frames* b200icp_frames_create(int n_scans) {
+  if (n_scans < 0) return nullptr;
+  b200icp_frames* f = new b200icp_frames();
+  f->scans.resize((size_t)n_scans);
+  return f;
+}
+
+void b200icp_frames_destroy(b200icp_frames* f) { delete f; }
+
+int b200icp_frames_add(b200icp_frames* f, int scan, const double transMat[16], int type) {
+  if (!f || !transMat || scan < 0 || scan >= (int)f->scans.size())
+    return b200icp_set_error_(B200ICP_EINVAL, "frames_add: bad argument");
+  Frame fr;
+  memcpy(fr.m, transMat, sizeof fr.m);
+  fr.type = type;
+  f->scans[(size_t)scan].push_back(fr);
+  return B200ICP_OK;
+}
+
+int b200icp_frames_transform(b200icp_frames* f, int scan, const double* transmats, int type, int islum) {
+  // the frame part of Scan::transform (scan.cc:941-1000) for a BasicScan `scan`; transmats = current transMat of
+  // EVERY scan (16 doubles each, allScans order)
+  if (!f || !transmats || scan < 0 || scan >= (int)f->scans.size())
+    return b200icp_set_error_(B200ICP_EINVAL, "frames_transform: bad argument");
+  if (type == B200ICP_FRAME_INVALID) return B200ICP_OK;
+  const int n = (int)f->scans.size();
+  int found = 0;
+  switch (islum) {
+    case -1: break;
+    case 0:
+      for (int i = 0; i < n; ++i) {
+        if (i == scan) { found = i; b200icp_frames_add(f, i, transmats + 16 * i, type); }
+        else b200icp_frames_add(f, i, transmats + 16 * i, found == 0 ? B200ICP_FRAME_ICPINACTIVE : B200ICP_FRAME_INVALID);
+      }
+      break;
+    case 1: b200icp_frames_add(f, scan, transmats + 16 * scan, type); break;
+    case 2:
+      for (int i = 0; i < n; ++i) {
+        if (i == scan) {
+          found = i;
+          b200icp_frames_add(f, i, transmats + 16 * i, type);
+          b200icp_frames_add(f, 0, transmats, type);
+          continue;
+        }
+        if (found != 0) b200icp_frames_add(f, i, transmats + 16 * i, B200ICP_FRAME_INVALID);
+      }
+      break;
+    default: return b200icp_set_error_(B200ICP_EINVAL, "invalid point transformation mode");
+  }
+  return B200ICP_OK;
+}
+
+int b200icp_frames_count(const b200icp_frames* f, int scan) {
+  if (!f || scan < 0 || scan >= (int)f->scans.size()) return -1;
+  return (int)f->scans[(size_t)scan].size();
+}
+
+int b200icp_frames_get(const b200icp_frames* f, int scan, int k, double transMat[16], int* type) {
+  if (!f || scan < 0 || scan >= (int)f->scans.size() || k < 0 || k >= (int)f->scans[(size_t)scan].size())
+    return b200icp_set_error_(B200ICP_EINVAL, "frames_get: bad index");
+  const Frame& fr = f->scans[(size_t)scan][(size_t)k];
+  if (transMat) memcpy(transMat, fr.m, sizeof fr.m);
+  if (type) *type = fr.type;
+  return B200ICP_OK;
+}
+
+int b200icp_frames_save(const b200icp_frames* f, int scan, const char* path, int append) {
+  if (!f || !path || scan < 0 || scan >= (int)f->scans.size())
+    return b200icp_set_error_(B200ICP_EINVAL, "frames_save: bad argument");
+  std::ofstream file(path, append ? std::ios_base::app : std::ios_base::out);
+  if (!file) return b200icp_set_error_(B200ICP_EINVAL, (std::string("frames_save: cannot open ") + path).c_str());
+  for (const Frame& fr : f->scans[(size_t)scan]) {
+    for (int i = 0; i < 16; ++i) {
+      if (std::isnan(fr.m[i])) return b200icp_set_error_(B200ICP_EINVAL, "will not write out NAN value");
+      file << fr.m[i] << " ";
+    }
+    file << fr.type << '\n';
+  }
+  file << std::flush;
+  return file.good() ? B200ICP_OK : b200icp_set_error_(B200ICP_EINVAL, "frames_save: write failed");
+}
+
+}  // extern "C"

@@ -46,6 +46,7 @@ extern "C" {
 
 typedef struct b200icp_ctx b200icp_ctx;   /* one per host thread / CUDA stream            */
 typedef struct b200icp_scan b200icp_scan; /* device-resident scan: points + search grid   */
+typedef struct b200icp_frames b200icp_frames;   /* per-scan frame lists, see "scan files and frames" */
 
 /* ---- context ------------------------------------------------------------------------------ */
 int b200icp_create(int device, b200icp_ctx** out);
@@ -172,10 +173,12 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
  * scan i is moved by transMat_{i-1} * inv(transMatOrg_{i-1})), then match(previous or metascan, current).
  * transMatOrg = 16 doubles per scan: the pose each scan was loaded with (NULL: the transMat at entry).
  * meta != 0 matches against a metascan of all scans processed so far (the last max_num_metascans when > 0),
- * rebuilt after every scan like the reference.  iterations_out (may be NULL) receives n entries (entry 0 = 0). */
+ * rebuilt after every scan like the reference.  iterations_out (may be NULL) receives n entries (entry 0 = 0).
+ * frames (may be NULL) records what Scan::transform would have pushed with the default anim = -1: per match the
+ * start pose, the pose after iteration 0 and the end pose, for every scan (icp6D.cc:109, :258-279). */
 int b200icp_do_icp(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const b200icp_match_params* params,
                    int extrapolate_pose, int meta, int max_num_metascans, const double* transMatOrg,
-                   int* iterations_out);
+                   int* iterations_out, b200icp_frames* frames);
 
 /* ---- query-sharded match across GPUs (the reference's pICP split, scan.cc:1335-1342) --------
  * Every rank holds the whole model scan and a contiguous slice of the data scan.  The per-iteration sum of the
@@ -194,6 +197,11 @@ int b200icp_comm_connect_ipc(b200icp_ctx* ctx, int world, const void* all_handle
 int b200icp_comm_connect_local(b200icp_ctx* ctx, int world, b200icp_ctx* const* all_ctx);
 void* b200icp_comm_mailbox(b200icp_ctx* ctx);
 int b200icp_comm_destroy(b200icp_ctx* ctx);
+
+/* transMat of the data scan after every iteration of the context's last b200icp_match that produced a transform
+ * (16 doubles each, column-major like the reference): what Scan::transform would have pushed as frames
+ * (icp6D.cc:258-264, scan.cc:955-983).  Returns the number of iterations recorded (may exceed cap). */
+int b200icp_last_poses(b200icp_ctx* ctx, int cap, double* transmats);
 
 /* Per-iteration record of the context's last b200icp_match: device time of the correspondence kernel
  * and of the solve kernel (ms; zeros unless params.profile was set), the number of queries that needed
@@ -234,11 +242,33 @@ int b200icp_graph_from_poses(const double* rpos, int n_scans, double cldist2, in
 int b200icp_lum_fill_gb(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
                         int n_links, double max_dist_match2, double* G, double* B, uint64_t* npairs_out);
 int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const double* G, const double* B,
-                             double* sum_position_diff);
+                             double* sum_position_diff, b200icp_frames* frames);
 int b200icp_lum_graph_slam(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
                            int n_links, double max_dist_match2, int nr_it, double epsilon_lum,
-                           double* ret_out, int* iterations_out);
+                           double* ret_out, int* iterations_out, b200icp_frames* frames);
 void b200icp_matrix4_to_euler(const double m[16], double rPosTheta[3], double rPos[3]);
+
+/* ---- scan files and frames (the wire formats either side of the path; host only) -----------
+ *   b200icp_read_uos     ScanIO_uos / readASCII (src/scanio/helper.cc:577-835): "x y z" per line, '#' comments,
+ *                        up to 10 unparsable lines tolerated at the top, \n or \r\n.  *xyz_out is malloc'ed
+ *                        (n rows of 3 doubles); release it with b200icp_free.  Parsed in parallel chunks.
+ *   b200icp_read_pose    scanNNN.pose: position, then Euler angles in DEGREES -> radians (helper.cc:228-232)
+ *   b200icp_frames_*     per-scan frame lists (BasicScan::m_frames); _transform applies the frame rule of
+ *                        Scan::transform (src/slam6d/scan.cc:941-1000) given the current transMat of every scan;
+ *                        _save writes scanNNN.frames exactly like BasicScan::saveFrames (basicScan.cc:902-917):
+ *                        16 doubles in the default ostream format, each followed by a blank, then the type. */
+enum { B200ICP_FRAME_INVALID = 0, B200ICP_FRAME_ICP = 1, B200ICP_FRAME_ICPINACTIVE = 2, B200ICP_FRAME_LUM = 3,
+       B200ICP_FRAME_ELCH = 4 };   /* Scan::AlgoType, include/slam6d/scan.h:126 */
+int b200icp_read_uos(const char* path, double** xyz_out, size_t* n_out);
+int b200icp_read_pose(const char* path, double rPos[3], double rPosTheta[3]);
+void b200icp_free(void* p);
+b200icp_frames* b200icp_frames_create(int n_scans);
+void b200icp_frames_destroy(b200icp_frames* frames);
+int b200icp_frames_add(b200icp_frames* frames, int scan, const double transMat[16], int type);
+int b200icp_frames_transform(b200icp_frames* frames, int scan, const double* transmats, int type, int islum);
+int b200icp_frames_count(const b200icp_frames* frames, int scan);
+int b200icp_frames_get(const b200icp_frames* frames, int scan, int k, double transMat[16], int* type);
+int b200icp_frames_save(const b200icp_frames* frames, int scan, const char* path, int append);
 
 /* ---- normals --------------------------------------------------------------------------------
  * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):

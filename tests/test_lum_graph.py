@@ -102,7 +102,13 @@ def test_graph_slam_matches_oracle(icp, ctx, n_scans, nr_it):
     for d, t in zip(dev, T):
         d.set_pose(t, None)
     lum = icp.lum6DEuler(ctx, max_dist_match_lum=25.0, epsilon_lum=1e-3)
-    ret, it = lum.doGraphSlam6D(icp.Graph(links, n_scans), dev, nr_it)
+    frames = icp.Frames(n_scans)
+    ret, it = lum.doGraphSlam6D(icp.Graph(links, n_scans), dev, nr_it, frames=frames)
+    # transformToEuler(.., LUM, 1) for every scan but the last, (.., LUM, 2) for the last one, which also pushes a
+    # frame on scan 0 (lum6Deuler.cc:447-451, scan.cc:986-999)
+    assert [len(frames.get(k)) for k in range(n_scans)] == [it] * n_scans
+    assert all(t == icp.FRAME_LUM for k in range(n_scans) for _, t in frames.get(k))
+    assert np.array_equal(frames.get(n_scans - 1)[-1][0], dev[n_scans - 1].get_pose()[0])
     want = orclib.port_lum_graph_slam(scans, links, 625.0, nr_it, 1e-3, T)
     assert it == want["iterations"]
     assert abs(ret - want["ret"]) <= 1e-7 * max(1.0, abs(want["ret"]))

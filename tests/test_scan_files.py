@@ -1,0 +1,122 @@
+"""Wire formats either side of the path: uos point files, .pose files, .frames files and the
+frame rule of Scan::transform.  Host only."""
+import os
+
+import numpy as np
+import pytest
+
+REF_DAT = "/root/reference/dat"          # present in the build container only; never on the GPU box
+
+
+def _write(path, text):
+    with open(path, "w", newline="") as f:
+        f.write(text)
+
+
+def test_read_uos_plain_and_decorated(icp, tmp_path):
+    rng = np.random.default_rng(3)
+    pts = np.round(rng.normal(0, 300, (5000, 3)), 4)
+    p = tmp_path / "scan000.3d"
+    _write(p, "".join("%s %s %s\n" % tuple(repr(float(v)) for v in row) for row in pts))
+    assert np.array_equal(icp.read_uos(p), pts)
+    # comments, blank lines, tabs, several blanks, CRLF, explicit signs and exponents (handle_line, helper.cc:577-640)
+    _write(p, "# header comment\r\n\r\n  1 2\t3\r\n+4.5   -6e1 7.25 # trailing comment\r\n\t\n8 9 10")
+    assert np.array_equal(icp.read_uos(p), [[1, 2, 3], [4.5, -60, 7.25], [8, 9, 10]])
+    _write(p, "")
+    assert icp.read_uos(p).shape == (0, 3)
+    with pytest.raises(icp.B200ICPError):
+        icp.read_uos(tmp_path / "missing.3d")
+
+
+def test_read_uos_header_rule(icp, tmp_path):
+    p = tmp_path / "s.3d"
+    # up to 10 unparsable lines at the top are skipped (helper.cc:752-822) ...
+    _write(p, "garbage line\n" * 10 + "1 2 3\n")
+    assert np.array_equal(icp.read_uos(p), [[1, 2, 3]])
+    # ... the 11th is fatal
+    _write(p, "garbage line\n" * 11 + "1 2 3\n")
+    with pytest.raises(icp.B200ICPError):
+        icp.read_uos(p)
+    # once a line has been handled (a point, but also a comment or an empty line) every bad line is fatal
+    for text in ("1 2 3\nbad\n", "# c\nbad\n1 2 3\n", "1 2 3\n1 2\n", "1 2 3\n1 2 3 4\n", "1 2 3\n1 2 x3\n"):
+        _write(p, text)
+        with pytest.raises(icp.B200ICPError):
+            icp.read_uos(p)
+    # wrong arity inside the header window is just one of the tolerated lines
+    _write(p, "1 2\n1 2 3 4\n5 6 7\n")
+    assert np.array_equal(icp.read_uos(p), [[5, 6, 7]])
+
+
+def test_read_uos_large_file_parallel_chunks(icp, tmp_path):
+    rng = np.random.default_rng(4)
+    pts = rng.normal(0, 1000, (120000, 3))
+    p = tmp_path / "big.3d"
+    _write(p, "".join("%.17g %.17g %.17g\n" % tuple(row) for row in pts))     # > 1 MiB: parsed by several threads
+    assert os.path.getsize(p) > (1 << 20)
+    assert np.array_equal(icp.read_uos(p), pts)                               # round-trip exact, order preserved
+    with open(p, "a") as f:
+        f.write("oops\n")
+    with pytest.raises(icp.B200ICPError):
+        icp.read_uos(p)
+
+
+def test_read_pose_degrees_to_radians(icp, tmp_path):
+    p = tmp_path / "scan001.pose"
+    _write(p, "-3.10605 -7.50803 156.917\n1.35694 -0.852409 -0.56224\n")       # the reference's dat/scan001.pose
+    pos, th = icp.read_pose(p)
+    assert np.array_equal(pos, [-3.10605, -7.50803, 156.917])
+    np.testing.assert_allclose(th, np.deg2rad([1.35694, -0.852409, -0.56224]), rtol=1e-15)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DAT), reason="reference dat/ not present")
+def test_read_reference_dat_scans(icp):
+    for k in range(3):
+        got = icp.read_uos(os.path.join(REF_DAT, "scan%03d.3d" % k))
+        assert got.shape == (81360, 3)                                         # wc -l dat/scan00*.3d
+        if k == 1:
+            assert np.array_equal(got, np.loadtxt(os.path.join(REF_DAT, "scan001.3d")))
+        pos, th = icp.read_pose(os.path.join(REF_DAT, "scan%03d.pose" % k))
+        assert np.all(np.isfinite(pos)) and np.all(np.abs(th) < np.pi)
+
+
+def test_frame_rule_of_scan_transform(icp):
+    I, A, L, X = icp.FRAME_ICPINACTIVE, icp.FRAME_ICP, icp.FRAME_LUM, icp.FRAME_INVALID
+    poses = np.stack([np.arange(16.0) + 100 * k for k in range(4)])
+    fr = icp.Frames(4)
+    fr.transform(2, poses, A, 0)         # islum 0: everybody gets a frame (scan.cc:955-983)
+    assert [fr.get(k)[0][1] for k in range(4)] == [I, I, A, X]
+    assert all(np.array_equal(fr.get(k)[0][0], poses[k]) for k in range(4))
+    fr.transform(0, poses, A, 0)         # `found` stays 0 for scan 0: the others count as inactive
+    assert [fr.get(k)[1][1] for k in range(4)] == [A, I, I, I]
+    fr.transform(1, poses, A, -1)        # islum -1: nothing
+    fr.transform(1, poses, X, 0)         # type INVALID: nothing (scan.cc:941)
+    assert [len(fr.get(k)) for k in range(4)] == [2, 2, 2, 2]
+    fr.transform(1, poses, L, 1)         # islum 1: only this scan
+    assert [len(fr.get(k)) for k in range(4)] == [2, 3, 2, 2] and fr.get(1)[2][1] == L
+    fr.transform(2, poses, L, 2)         # islum 2: this scan and scan 0, INVALID for the scans after it
+    assert [len(fr.get(k)) for k in range(4)] == [3, 3, 3, 3]
+    assert [fr.get(k)[-1][1] for k in range(4)] == [L, L, L, X]
+    with pytest.raises(icp.B200ICPError):
+        fr.transform(7, poses, A, 0)
+
+
+def test_frames_file_format(icp, tmp_path):
+    fr = icp.Frames(2)
+    m = np.array([1, 0, 0, 0, 0, 0.99999994, -1.5e-7, 0, 0, 1.25e-5, 1, 0, -3.10605, 123456789.0, 156.917, 1])
+    fr.add(1, m, icp.FRAME_ICP)
+    fr.add(1, m * 2, icp.FRAME_LUM)
+    p = tmp_path / "scan001.frames"
+    fr.save(1, p)
+    lines = open(p).read().split("\n")
+    assert lines[-1] == "" and len(lines) == 3
+    # operator<<(ostream&, const double[16]) (globals.icc:123-132): default precision (%g), blank after EVERY value
+    assert lines[0] == "".join("%g " % v for v in m) + "1"
+    assert lines[1] == "".join("%g " % v for v in 2 * m) + "3"
+    fr.save(1, p, append=True)
+    assert len(open(p).read().split("\n")) == 5
+    fr.save(0, p)                                     # a scan without frames writes an empty file
+    assert open(p).read() == ""
+    bad = icp.Frames(1)
+    bad.add(0, np.full(16, np.nan), icp.FRAME_ICP)
+    with pytest.raises(icp.B200ICPError):
+        bad.save(0, p)
