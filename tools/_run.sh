@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_multigpu.py -m gpu -x -q 2>&1 | tail -15
