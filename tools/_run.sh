@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_multigpu.py -m gpu -x -q 2>&1 | tail -15
+PPC=4 bash tools/ab.sh base dyn1 hy4 hy6 hy7
