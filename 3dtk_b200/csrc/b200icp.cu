@@ -916,6 +916,10 @@ int b200icp_debug_tile_stats(unsigned long long* out8) {
 #endif
 
 #ifdef B200_TIMING
+// debug builds only: per-block (start, tile loop done, partials stored, SM id) of the last fused iteration launch
+int b200icp_debug_blocks(unsigned long long* out, int nblocks) {
+  return cudaMemcpyFromSymbol(out, g_blk, (size_t)nblocks * 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
 // debug builds only: the in-kernel timeline of the last iteration (globaltimer ns), see tl_mark
 int b200icp_debug_timing(unsigned long long* out32) {
   return cudaMemcpyFromSymbol(out32, g_tl, 32 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;

@@ -22,8 +22,17 @@ __device__ unsigned long long g_tl[32];
 __device__ __forceinline__ void tl_mark(int k) {
   if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tl[k] = t; }
 }
+// per-block record of the fused iteration kernel: [block][0..3] = start, tile loop done, partials stored, SM id
+__device__ unsigned long long g_blk[2048][4];
+__device__ __forceinline__ void blk_mark(int k) {
+  if (threadIdx.x == 0 && blockIdx.x < 2048) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_blk[blockIdx.x][k] = t;
+    if (k == 0) { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); g_blk[blockIdx.x][3] = s; }
+  }
+}
 #else
 __device__ __forceinline__ void tl_mark(int) {}
+__device__ __forceinline__ void blk_mark(int) {}
 #endif
 
 struct XfSmem {
@@ -372,6 +381,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   IterSmem<NS>& sm = *reinterpret_cast<IterSmem<NS>*>(dyn_smem);
   __shared__ XfSmem xf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  blk_mark(0);
   load_xf(xf, st);
   const unsigned iter_salt = (unsigned)st->iter * 0x9E3779B9u;
   // a query may skip its search while it has moved less than its certified budget (nn_search.cuh);
@@ -472,6 +482,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   // leftovers: merge the warps' partial queues so the remaining searches run in full batches
   if (lane == 0) sm.left_count[warp] = qcount;
   __syncthreads();
+  blk_mark(1);
   {
     int off = 0, total = 0;
 #pragma unroll
@@ -487,6 +498,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   }
 
   block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+  blk_mark(2);
   if (lane == 0 && stage2) atomicAdd(stage2_counter, stage2);
   if (lane == 0 && searches) atomicAdd(stage2_counter + 1, searches);
   // ---- the last block to get here reduces all partials and runs the solve (no second launch)
