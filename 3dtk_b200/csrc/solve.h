@@ -319,7 +319,7 @@ B2_HD void set_translation_from_centroids(double* M, const double* cm, const dou
   M[14] = cm[2] - M[2] * cd[0] - M[6] * cd[1] - M[10] * cd[2];
 }
 
-// ---- the four minimizers ---------------------------------------------------------------------------
+// ---- the minimizers ---------------------------------------------------------------------------
 // All take moments `mom` about shift origin `o` and write a column-major alignxf.  Return the RMS the
 // reference's Align returns (sqrt(sum/n)), or -1.0 when a Cholesky pivot check fails.
 
@@ -393,6 +393,98 @@ B2_HD double solve_svd(const double* mom, const double* o, double* alignxf) {
   double cmo[3] = {cm[0] + o[0], cm[1] + o[1], cm[2] + o[2]};
   double cdo[3] = {cd[0] + o[0], cd[1] + o[1], cd[2] + o[2]};
   set_translation_from_centroids(alignxf, cmo, cdo);
+  return sqrt(mom[MP_D2] * inv);
+}
+
+// ORTHO (icp6Dortho.cc:41-153, Horn/Hilden/Negahdaripour orthonormal matrices): H = sum m' d'^T (centred),
+// R = H (H^T H)^(-1/2) through the eigen-decomposition of the symmetric H^T H, t = cm - R cd.
+B2_HD double solve_ortho(const double* mom, const double* o, double* alignxf) {
+  const double n = mom[MP_N];
+  const double inv = 1.0 / n;
+  double cm[3], cd[3];
+  for (int i = 0; i < 3; ++i) { cm[i] = mom[MP_M + i] * inv; cd[i] = mom[MP_D + i] * inv; }
+  double H[3][3], HH[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) H[i][j] = mom[MP_DM + 3 * j + i] - n * cm[i] * cd[j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) HH[i][j] = H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j];
+  jacobi_eig<3>(HH, V);
+  double W[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // sum_k v_k v_k^T / sqrt(lambda_k)
+  for (int k = 0; k < 3; ++k) {
+    const double f = 1.0 / sqrt(HH[k][k]);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) W[i][j] += V[i][k] * V[j][k] * f;
+  }
+  m4_identity(alignxf);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) alignxf[4 * c + r] = H[r][0] * W[0][c] + H[r][1] * W[1][c] + H[r][2] * W[2][c];
+  double cmo[3] = {cm[0] + o[0], cm[1] + o[1], cm[2] + o[2]};
+  double cdo[3] = {cd[0] + o[0], cd[1] + o[1], cd[2] + o[2]};
+  set_translation_from_centroids(alignxf, cmo, cdo);
+  return sqrt(mom[MP_D2] * inv);
+}
+
+// DUAL (icp6Ddual.cc:41-150, Walker/Shao/Volz dual quaternions).  Every entry of the reference's C1 / C2 is
+// linear in M = sum m d^T and in sum m, sum d (Cm d = m x d, Cm Cd = d m^T - (m.d) I), so the per-pair walk
+// collapses to the moments.  Evaluated in the shifted frame (origin o) and mapped back: t = t' + o - R o -- the
+// least-squares optimum is the same, the reference evaluates it with absolute coordinates.
+// The rotation quaternion is the eigenvector of A with the largest |eigenvalue| (the reference takes column 1 of
+// newmat's SVD of the symmetric A, i.e. the largest singular value).
+B2_HD double solve_dual(const double* mom, const double* o, double* alignxf) {
+  const double n = mom[MP_N];
+  const double inv = 1.0 / n;
+  double M[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M[i][j] = mom[MP_DM + 3 * j + i];      // sum m_i d_j
+  const double tr = M[0][0] + M[1][1] + M[2][2];
+  const double cr[3] = {M[1][2] - M[2][1], M[2][0] - M[0][2], M[0][1] - M[1][0]};   // sum m x d
+  double C1[4][4], C2[4][4];
+  C1[0][0] = tr;
+  for (int i = 0; i < 3; ++i) { C1[0][i + 1] = -cr[i]; C1[i + 1][0] = -cr[i]; }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C1[i + 1][j + 1] = M[i][j] + M[j][i] - (i == j ? tr : 0.0);
+  const double dm[3] = {mom[MP_M] - mom[MP_D], mom[MP_M + 1] - mom[MP_D + 1], mom[MP_M + 2] - mom[MP_D + 2]};
+  const double sp[3] = {mom[MP_M] + mom[MP_D], mom[MP_M + 1] + mom[MP_D + 1], mom[MP_M + 2] + mom[MP_D + 2]};
+  C2[0][0] = 0.0;
+  for (int i = 0; i < 3; ++i) { C2[0][i + 1] = dm[i]; C2[i + 1][0] = -dm[i]; }
+  // -(Cd + Cm) = -[sp]x
+  C2[1][1] = 0.0;    C2[1][2] = sp[2];  C2[1][3] = -sp[1];
+  C2[2][1] = -sp[2]; C2[2][2] = 0.0;    C2[2][3] = sp[0];
+  C2[3][1] = sp[1];  C2[3][2] = -sp[0]; C2[3][3] = 0.0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { C1[i][j] *= -2.0; C2[i][j] *= 2.0; }
+  double A[4][4], V[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double t = 0.0;
+      for (int k = 0; k < 4; ++k) t += C2[k][i] * C2[k][j];
+      A[i][j] = (t * (0.5 * inv) - C1[i][j] - C1[j][i]) * 0.5;
+    }
+  jacobi_eig<4>(A, V);
+  int best = 0;
+  for (int k = 1; k < 4; ++k) if (fabs(A[k][k]) > fabs(A[best][best])) best = k;
+  const double q0 = V[0][best], q[3] = {V[1][best], V[2][best], V[3][best]};
+  const double qd[4] = {q0, q[0], q[1], q[2]};
+  double sv[4];
+  for (int i = 0; i < 4; ++i) {
+    double t = 0.0;
+    for (int k = 0; k < 4; ++k) t += C2[i][k] * qd[k];
+    sv[i] = -t * (0.5 * inv);
+  }
+  // p = Q s with Q = [[q0, q^T], [-q, q0 I + Cq]]; translation = p[1..3]
+  const double tp[3] = {-q[0] * sv[0] + q0 * sv[1] - q[2] * sv[2] + q[1] * sv[3],
+                        -q[1] * sv[0] + q[2] * sv[1] + q0 * sv[2] - q[0] * sv[3],
+                        -q[2] * sv[0] - q[1] * sv[1] + q[0] * sv[2] + q0 * sv[3]};
+  const double qq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  double R[3][3];
+  const double Cq[3][3] = {{0, -q[2], q[1]}, {q[2], 0, -q[0]}, {-q[1], q[0], 0}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i][j] = (i == j ? q0 * q0 - qq : 0.0) + 2.0 * q[i] * q[j] + 2.0 * q0 * Cq[i][j];
+  m4_identity(alignxf);
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) alignxf[4 * c + r] = R[r][c];
+  for (int r = 0; r < 3; ++r)
+    alignxf[12 + r] = tp[r] + o[r] - (R[r][0] * o[0] + R[r][1] * o[1] + R[r][2] * o[2]);
   return sqrt(mom[MP_D2] * inv);
 }
 
@@ -484,6 +576,8 @@ B2_HD double solve_any(int algo, const double* mom, const double* o, int napx_we
   switch (algo) {
     case 1: return solve_quat(mom, o, alignxf);
     case 2: return solve_svd(mom, o, alignxf);
+    case 3: return solve_ortho(mom, o, alignxf);
+    case 4: return solve_dual(mom, o, alignxf);
     case 6: return solve_apx(mom, o, alignxf);
     case 10: return solve_napx(mom, o, napx_weighted, alignxf);
     default: return -2.0;

@@ -37,6 +37,8 @@ extern "C" {
 /* icp6Dminimizer::getAlgorithmID() values (include/slam6d/icp6D{quat,svd,apx,napx}.h) */
 #define B200ICP_ALGO_QUAT 1
 #define B200ICP_ALGO_SVD 2
+#define B200ICP_ALGO_ORTHO 3  /* icp6D_ORTHO (src/slam6d/icp6Dortho.cc), same pair moments as QUAT/SVD */
+#define B200ICP_ALGO_DUAL 4   /* icp6D_DUAL  (src/slam6d/icp6Ddual.cc),  same pair moments             */
 #define B200ICP_ALGO_APX 6
 #define B200ICP_ALGO_NAPX 10
 

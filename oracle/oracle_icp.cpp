@@ -609,6 +609,88 @@ double align_napx(long n, const double* p1, const double* p2, const double* nrm,
 
 }  // namespace
 
+// icp6D_ORTHO::Align (icp6Dortho.cc:41-153): literal per-pair walk in absolute coordinates
+double align_ortho(long n, const double* p1, const double* p2, const double* cm, const double* cd, double* M) {
+  double sum = 0, H[9] = {0}, HH[9], V[9];
+  for (long i = 0; i < n; ++i) {
+    double m[3], d[3];
+    for (int k = 0; k < 3; ++k) { m[k] = p1[3 * i + k] - cm[k]; d[k] = p2[3 * i + k] - cd[k]; }
+    sum += sq(p1[3 * i] - p2[3 * i]) + sq(p1[3 * i + 1] - p2[3 * i + 1]) + sq(p1[3 * i + 2] - p2[3 * i + 2]);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) H[3 * a + b] += m[a] * d[b];
+  }
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) HH[3 * a + b] = H[a] * H[b] + H[3 + a] * H[3 + b] + H[6 + a] * H[6 + b];
+  jacobi_sym(3, HH, V);
+  double W[9] = {0};
+  for (int k = 0; k < 3; ++k)
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) W[3 * a + b] += V[3 * a + k] * V[3 * b + k] / sqrt(HH[4 * k]);
+  double R[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) R[a][b] = H[3 * a] * W[b] + H[3 * a + 1] * W[3 + b] + H[3 * a + 2] * W[6 + b];
+  rot_to_matrix(R, cm, cd, M);
+  return sqrt(sum / (double)n);
+}
+
+// icp6D_DUAL::Align (icp6Ddual.cc:41-150): C1, C2 accumulated pair by pair exactly as written there
+double align_dual(long n, const double* p1, const double* p2, double* M) {
+  double sum = 0, C1[16] = {0}, C2[16] = {0};
+  for (long i = 0; i < n; ++i) {
+    const double* m = p1 + 3 * i;
+    const double* d = p2 + 3 * i;
+    sum += sq(m[0] - d[0]) + sq(m[1] - d[1]) + sq(m[2] - d[2]);
+    double Cm[3][3] = {{0, -m[2], m[1]}, {m[2], 0, -m[0]}, {-m[1], m[0], 0}};
+    double Cd[3][3] = {{0, -d[2], d[1]}, {d[2], 0, -d[0]}, {-d[1], d[0], 0}};
+    C1[0] += m[0] * d[0] + m[1] * d[1] + m[2] * d[2];
+    for (int j = 0; j < 3; ++j) {
+      double mtCd = m[0] * Cd[0][j] + m[1] * Cd[1][j] + m[2] * Cd[2][j];
+      double Cmd = Cm[j][0] * d[0] + Cm[j][1] * d[1] + Cm[j][2] * d[2];
+      C1[1 + j] += -mtCd;
+      C1[4 * (1 + j)] += -Cmd;
+      C2[1 + j] += -d[j] + m[j];
+      C2[4 * (1 + j)] += d[j] - m[j];
+      for (int k = 0; k < 3; ++k) {
+        double CmCd = Cm[j][0] * Cd[0][k] + Cm[j][1] * Cd[1][k] + Cm[j][2] * Cd[2][k];
+        C1[4 * (1 + j) + 1 + k] += m[j] * d[k] + CmCd;
+        C2[4 * (1 + j) + 1 + k] += -Cd[j][k] - Cm[j][k];
+      }
+    }
+  }
+  for (int k = 0; k < 16; ++k) { C1[k] *= -2; C2[k] *= 2; }
+  double A[16], V[16];
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      double t = 0;
+      for (int k = 0; k < 4; ++k) t += C2[4 * k + a] * C2[4 * k + b];
+      A[4 * a + b] = (t * 1.0 / (2 * n) - C1[4 * a + b] - C1[4 * b + a]) * 0.5;
+    }
+  jacobi_sym(4, A, V);
+  int best = 0;   // SVD of a symmetric matrix: column 1 of U belongs to the largest |eigenvalue|
+  for (int k = 1; k < 4; ++k) if (fabs(A[5 * k]) > fabs(A[5 * best])) best = k;
+  double qd[4] = {V[best], V[4 + best], V[8 + best], V[12 + best]};
+  double q[3] = {qd[1], qd[2], qd[3]};
+  double s[4];
+  for (int a = 0; a < 4; ++a) {
+    double t = 0;
+    for (int k = 0; k < 4; ++k) t += C2[4 * a + k] * qd[k];
+    s[a] = t * (-1.0) / (2 * n);
+  }
+  double Cq[3][3] = {{0, -q[2], q[1]}, {q[2], 0, -q[0]}, {-q[1], q[0], 0}};
+  double tr[3];
+  for (int a = 0; a < 3; ++a) {
+    tr[a] = -q[a] * s[0];
+    for (int b = 0; b < 3; ++b) tr[a] += ((a == b ? qd[0] : 0.0) + Cq[a][b]) * s[1 + b];
+  }
+  double qq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  for (int k = 0; k < 16; ++k) M[k] = 0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      M[4 * b + a] = (a == b ? qd[0] * qd[0] - qq : 0.0) + q[a] * q[b] * 2 + Cq[a][b] * qd[0] * 2;
+  M[12] = tr[0]; M[13] = tr[1]; M[14] = tr[2]; M[15] = 1;
+  return sqrt(sum / (double)n);
+}
+
 extern "C" {
 
 // ---- math pins
@@ -715,6 +797,8 @@ double orc_align(int algo, long n, const double* p1, const double* p2, const dou
   switch (algo) {
     case 1: return align_quat(n, p1, p2, cm, cd, alignxf);
     case 2: return align_svd(n, p1, p2, cm, cd, alignxf);
+    case 3: return align_ortho(n, p1, p2, cm, cd, alignxf);
+    case 4: return align_dual(n, p1, p2, alignxf);
     case 6: return align_apx(n, p1, p2, cm, cd, alignxf);
     case 10: return align_napx(n, p1, p2, nrm, cd, napx_weighted, alignxf);
   }

@@ -28,6 +28,8 @@
 #include "slam6d/icp6Dquat.h"
 #include "slam6d/icp6Dsvd.h"
 #include "slam6d/icp6Dapx.h"
+#include "slam6d/icp6Dortho.h"
+#include "slam6d/icp6Ddual.h"
 #include "slam6d/icp6Dnapx.h"
 #include "slam6d/normals.h"
 #include "slam6d/globals.icc"
@@ -52,6 +54,8 @@ icp6Dminimizer* make_minimizer(int algo) {
   switch (algo) {
     case 1: return new icp6D_QUAT(true);
     case 2: return new icp6D_SVD(true);
+    case 3: return new icp6D_ORTHO(true);
+    case 4: return new icp6D_DUAL(true);
     case 6: return new icp6D_APX(true);
     case 10: return new icp6D_NAPX(true);
     default: return nullptr;

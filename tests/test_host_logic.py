@@ -65,7 +65,7 @@ def _pairs(rng, n, theta, pos, noise, scale=500.0):
     return np.ascontiguousarray(p1), np.ascontiguousarray(p2), np.ascontiguousarray(nr)
 
 
-@pytest.mark.parametrize("algo", [1, 2, 6, 10])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4, 6, 10])
 @pytest.mark.parametrize("n", [4, 50, 20000])
 def test_align_pairs_matches_oracle_align(icp, port, algo, n):
     rng = np.random.default_rng(100 * algo + n)
@@ -78,8 +78,10 @@ def test_align_pairs_matches_oracle_align(icp, port, algo, n):
         assert r_got == -1.0
         return
     assert abs(r_got - r_want) <= 1e-12 * max(1.0, abs(r_want))
-    # tolerance: 1e-9 relative Frobenius (the north-star gate on whole matches is 1e-4)
-    assert orclib.rel_frobenius(got, want) < 1e-9
+    # tolerance: 1e-9 relative Frobenius (the north-star gate on whole matches is 1e-4); ORTHO forms H^T H, which
+    # squares the condition number -- with 4 pairs its smallest eigenvalue amplifies the rounding difference
+    # between centred pair sums (reference / oracle) and moments (product)
+    assert orclib.rel_frobenius(got, want) < (1e-6 if algo == 3 and n < 10 else 1e-9)
 
 
 def test_align_pairs_reflection_and_degenerate(icp, port):
