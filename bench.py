@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--shard", default="pairs", choices=["pairs", "queries"],
                     help="pairs: one scan pair per GPU (weak scaling, default, north_star); queries: ONE pair, data\n"
                          "points split across GPUs, moments all-reduced inside the kernel over NVLink (strong scaling)")
+    ap.add_argument("--rows", action="store_true",
+                    help="instead of the configs[1] line: measure the SURVEY 8f rows (octree reduction, normals, LUM link,\n"
+                         "graph relaxation, metascan, uos reader), one JSON object per row (tests/rows_bench.py)")
     return ap.parse_args()
 
 
@@ -222,6 +225,12 @@ def cpu_reference_run(model, data, max_iter, steps, warmup):
 
 def main():
     a = parse()
+    if a.rows:   # single GPU, rank 0 only; the CPU arms of these rows execute the oracle, hence under tests/
+        if int(os.environ.get("RANK", "0")) == 0:
+            import runpy
+            runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "rows_bench.py"),
+                           run_name="__main__")
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

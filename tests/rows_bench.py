@@ -3,12 +3,13 @@
 GPU wall time through the C ABI with HOST buffers (copies included, after a warm-up call), algorithmic bytes and the
 bandwidth they imply against MEASURED_PEAKS.json, and the CPU arm (compiled reference `oracle/_ref` where the
 reference function compiles, otherwise the oracle port) timed on a bounded sample on this box's host cores.
-    python tools/bench_rows.py > profiles/rNN_rows_bench.json
-Not part of bench.py's contract (that is the configs[1] match); these are the per-row numbers DESIGN.md cites."""
+    python bench.py --rows > profiles/rNN_rows_bench.json        (bench.py runs this file)
+Lives under tests/ because its CPU arm executes the oracle libraries (test infrastructure); not part of bench.py's
+one-line contract (that is the configs[1] match) -- these are the per-row numbers DESIGN.md cites."""
 import importlib, json, os, sys, tempfile, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT, os.path.dirname(os.path.abspath(__file__))]
 import orclib
 icp = importlib.import_module("3dtk_b200")
 ctx = icp.Context(0)
