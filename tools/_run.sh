@@ -1,1 +1,3 @@
-CONFIG5_VOXEL=2.5 timeout 1500 python tools/config_scale.py 4 5 > gpurun_out/configs_full2.json 2> gpurun_out/configs_full2.err; tail -5 gpurun_out/configs_full2.err; cat gpurun_out/configs_full2.json | cut -c1-1600
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 400 python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | cut -c1-200
