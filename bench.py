@@ -21,6 +21,7 @@ no data-path collective ("scaling": "weak"); time = max over ranks.
 import argparse
 import ctypes as C
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -234,8 +235,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
-        import importlib.util   # by path: the package __init__ raises while the library is still missing
+    if rank == 0:   # by path: the package __init__ raises while the library is still missing
         spec = importlib.util.spec_from_file_location(
             "_b200icp_build", os.path.join(os.path.dirname(os.path.abspath(__file__)), "3dtk_b200", "build.py"))
         build = importlib.util.module_from_spec(spec)
