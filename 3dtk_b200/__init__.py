@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200ICP_LIB") or os.path.join(_HERE, "lib", "libb200icp.so")  # override: A/B builds
 
-ALGO_QUAT, ALGO_SVD, ALGO_ORTHO, ALGO_DUAL, ALGO_APX, ALGO_NAPX = 1, 2, 3, 4, 6, 10
+ALGO_QUAT, ALGO_SVD, ALGO_ORTHO, ALGO_DUAL, ALGO_HELIX, ALGO_APX, ALGO_NAPX = 1, 2, 3, 4, 5, 6, 10
 CLOSEST_POINT, CLOSEST_PLANE_SIMPLE = 0, 2
 
 E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "EEMPTY", -6: "ESTATE"}

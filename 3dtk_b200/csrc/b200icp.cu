@@ -738,8 +738,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
                   b200icp_match_result* result) {
   if (!ctx || !model || !data || !prm) return fail(B200ICP_EINVAL, "match: NULL argument");
   const int algo = prm->algo;
-  if (algo != 1 && algo != 2 && algo != 3 && algo != 4 && algo != 6 && algo != 10)
-    return fail(B200ICP_EINVAL, "match: algo must be 1 (QUAT), 2 (SVD), 3 (ORTHO), 4 (DUAL), 6 (APX) or 10 (NAPX)");
+  if (algo != 1 && algo != 2 && algo != 3 && algo != 4 && algo != 5 && algo != 6 && algo != 10)
+    return fail(B200ICP_EINVAL, "match: algo must be 1 (QUAT), 2 (SVD), 3 (ORTHO), 4 (DUAL), 5 (HELIX), 6 (APX) or 10 (NAPX)");
   if (prm->pairing_mode != B200ICP_CLOSEST_POINT && prm->pairing_mode != B200ICP_CLOSEST_PLANE_SIMPLE)
     return fail(B200ICP_EINVAL, "match: pairing mode not on the accelerated path");
   // reference ctor checks, icp6D.cc:67-78 (there: exit(1))

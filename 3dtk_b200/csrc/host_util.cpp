@@ -18,7 +18,7 @@ int b200icp_align_pairs(int algo, size_t n, const double* p1, const double* p2, 
                         const double centroid_m[3], const double centroid_d[3], double alignxf[16],
                         double* rms_out) {
   if (!p1 || !p2 || !alignxf) return B200ICP_EINVAL;
-  if (algo != 1 && algo != 2 && algo != 3 && algo != 4 && algo != 6 && algo != 10) return B200ICP_EINVAL;
+  if (algo != 1 && algo != 2 && algo != 3 && algo != 4 && algo != 5 && algo != 6 && algo != 10) return B200ICP_EINVAL;
   if (algo == 10 && !nrm) return B200ICP_EINVAL;
   if (n == 0) return B200ICP_EEMPTY;
   // Shift origin: the data-side centroid the caller already holds (any point near the cloud works).

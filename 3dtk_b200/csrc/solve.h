@@ -488,6 +488,80 @@ B2_HD double solve_dual(const double* mom, const double* o, double* alignxf) {
   return sqrt(mom[MP_D2] * inv);
 }
 
+// Gaussian elimination with partial pivoting, A x = b in place (x returned in b); false when singular.
+template <int N>
+B2_HD bool gauss_solve(double A[N][N], double* b) {
+  for (int c = 0; c < N; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < N; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (A[piv][c] == 0.0) return false;
+    if (piv != c) {
+      for (int k = 0; k < N; ++k) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+      const double t = b[c]; b[c] = b[piv]; b[piv] = t;
+    }
+    for (int r = c + 1; r < N; ++r) {
+      const double f = A[r][c] / A[c][c];
+      for (int k = c; k < N; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = N - 1; r >= 0; --r) {
+    double t = b[r];
+    for (int k = r + 1; k < N; ++k) t -= A[r][k] * b[k];
+    b[r] = t / A[r][r];
+  }
+  return true;
+}
+
+// HELIX (icp6Dhelix.cc:48-205, Pottmann/Leopoldseder/Hofer): least squares over the linearised motion
+// x -> x + cs + c x x, then the helical motion with that axis, angle atan|c| and pitch (computeRt).  The 6x6
+// system only needs sum p2, sum p2 p2^T, sum p2 x p1 and sum (p2 - p1): all in the pair moments.  Solved in the
+// shifted frame (the family of linearised motions does not depend on the origin, the helical motion is a
+// geometric object) and mapped back: t = t' + o - R o.
+B2_HD double solve_helix(const double* mom, const double* o, double* alignxf) {
+  const double n = mom[MP_N];
+  const double* D = mom + MP_D;
+  const double* DM = mom + MP_DM;      // sum b_i a_j, b = p2 - o, a = p1 - o
+  const double xx = mom[MP_DD], xy = mom[MP_DD + 1], xz = mom[MP_DD + 2], yy = mom[MP_DD + 3], yz = mom[MP_DD + 4],
+               zz = mom[MP_DD + 5];
+  double B[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) B[i][j] = 0.0;
+  B[0][0] = zz + yy; B[1][1] = zz + xx; B[2][2] = xx + yy;
+  B[0][1] = B[1][0] = -xy; B[0][2] = B[2][0] = -xz; B[1][2] = B[2][1] = -yz;
+  B[3][3] = B[4][4] = B[5][5] = n;
+  B[0][4] = B[4][0] = -D[2]; B[1][3] = B[3][1] = D[2];
+  B[0][5] = B[5][0] = D[1];  B[2][3] = B[3][2] = -D[1];
+  B[2][4] = B[4][2] = D[0];  B[1][5] = B[5][1] = -D[0];
+  double x[6] = {DM[7] - DM[5], DM[2] - DM[6], DM[3] - DM[1],
+                 mom[MP_D] - mom[MP_M], mom[MP_D + 1] - mom[MP_M + 1], mom[MP_D + 2] - mom[MP_M + 2]};
+  gauss_solve<6>(B, x);
+  const double c[3] = {-x[0], -x[1], -x[2]}, cs[3] = {-x[3], -x[4], -x[5]};
+  const double cl = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  const double chk = c[0] * cs[0] + c[1] * cs[1] + c[2] * cs[2];
+  const double angle = atan(cl);
+  const double g[3] = {c[0] / cl, c[1] / cl, c[2] / cl};
+  const double sa = sin(-angle / 2), b0 = cos(-angle / 2), b1 = g[0] * sa, b2 = g[1] * sa, b3 = g[2] * sa;
+  double R[3][3];
+  R[0][0] = b0 * b0 + b1 * b1 - b2 * b2 - b3 * b3; R[0][1] = 2 * (b1 * b2 + b0 * b3); R[0][2] = 2 * (b1 * b3 - b0 * b2);
+  R[1][0] = 2 * (b1 * b2 - b0 * b3); R[1][1] = b0 * b0 - b1 * b1 + b2 * b2 - b3 * b3; R[1][2] = 2 * (b2 * b3 + b0 * b1);
+  R[2][0] = 2 * (b1 * b3 + b0 * b2); R[2][1] = 2 * (b2 * b3 - b0 * b1); R[2][2] = b0 * b0 - b1 * b1 - b2 * b2 + b3 * b3;
+  const double nn = b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i][j] /= nn;
+  const double skew = chk / (cl * cl);
+  const double gs[3] = {(cs[0] - c[0] * skew) / cl, (cs[1] - c[1] * skew) / cl, (cs[2] - c[2] * skew) / cl};
+  const double pt[3] = {g[1] * gs[2] - g[2] * gs[1], g[2] * gs[0] - g[0] * gs[2], g[0] * gs[1] - g[1] * gs[0]};
+  m4_identity(alignxf);
+  for (int cc = 0; cc < 3; ++cc)
+    for (int r = 0; r < 3; ++r) alignxf[4 * cc + r] = R[r][cc];
+  for (int r = 0; r < 3; ++r) {
+    const double tp = -(R[r][0] * pt[0] + R[r][1] * pt[1] + R[r][2] * pt[2]) + g[r] * (skew * angle) + pt[r];
+    alignxf[12 + r] = tp + o[r] - (R[r][0] * o[0] + R[r][1] * o[1] + R[r][2] * o[2]);
+  }
+  return sqrt(mom[MP_D2] / n);
+}
+
 // APX (icp6Dapx.cc:35-133): A x = B over centred data-side second moments.
 B2_HD double solve_apx(const double* mom, const double* o, double* alignxf) {
   const double n = mom[MP_N];
@@ -578,6 +652,7 @@ B2_HD double solve_any(int algo, const double* mom, const double* o, int napx_we
     case 2: return solve_svd(mom, o, alignxf);
     case 3: return solve_ortho(mom, o, alignxf);
     case 4: return solve_dual(mom, o, alignxf);
+    case 5: return solve_helix(mom, o, alignxf);
     case 6: return solve_apx(mom, o, alignxf);
     case 10: return solve_napx(mom, o, napx_weighted, alignxf);
     default: return -2.0;

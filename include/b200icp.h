@@ -39,6 +39,7 @@ extern "C" {
 #define B200ICP_ALGO_SVD 2
 #define B200ICP_ALGO_ORTHO 3  /* icp6D_ORTHO (src/slam6d/icp6Dortho.cc), same pair moments as QUAT/SVD */
 #define B200ICP_ALGO_DUAL 4   /* icp6D_DUAL  (src/slam6d/icp6Ddual.cc),  same pair moments             */
+#define B200ICP_ALGO_HELIX 5  /* icp6D_HELIX (src/slam6d/icp6Dhelix.cc), same pair moments             */
 #define B200ICP_ALGO_APX 6
 #define B200ICP_ALGO_NAPX 10
 

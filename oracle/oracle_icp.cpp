@@ -691,6 +691,52 @@ double align_dual(long n, const double* p1, const double* p2, double* M) {
   return sqrt(sum / (double)n);
 }
 
+static bool solve6(double A[6][6], double* b);   // defined with the LUM link below
+
+// icp6D_HELIX::Align + computeRt (icp6Dhelix.cc:48-205): sums over the pairs in absolute coordinates as written
+// there; the 6x6 inverse (newmat .i()) by Gaussian elimination with partial pivoting
+double align_helix(long n, const double* p1, const double* p2, double* M) {
+  double B[6][3] = {{0}}, bd[6] = {0}, sum = 0;
+  for (long i = 0; i < n; ++i) {
+    double x = p2[3 * i], y = p2[3 * i + 1], z = p2[3 * i + 2];
+    B[4][0] += -z; B[3][1] += z; B[5][0] += y; B[3][2] += -y; B[4][2] += x; B[5][1] += -x;
+    B[0][0] += z * z + y * y; B[1][0] += y * -x; B[2][0] += -z * x;
+    B[1][1] += z * z + x * x; B[2][1] += z * -y; B[2][2] += x * x + y * y;
+    double dx = x - p1[3 * i], dy = y - p1[3 * i + 1], dz = z - p1[3 * i + 2];
+    bd[0] += -z * dy + y * dz; bd[1] += z * dx - x * dz; bd[2] += -y * dx + x * dy;
+    bd[3] += dx; bd[4] += dy; bd[5] += dz;
+    sum += dx * dx + dy * dy + dz * dz;
+  }
+  double A[6][6] = {{0}};
+  A[3][3] = A[4][4] = A[5][5] = (double)n;
+  A[0][4] = A[4][0] = B[4][0]; A[1][3] = A[3][1] = B[3][1]; A[0][5] = A[5][0] = B[5][0];
+  A[2][3] = A[3][2] = B[3][2]; A[2][4] = A[4][2] = B[4][2]; A[1][5] = A[5][1] = B[5][1];
+  A[0][1] = A[1][0] = B[1][0]; A[0][2] = A[2][0] = B[2][0]; A[1][2] = A[2][1] = B[2][1];
+  A[0][0] = B[0][0]; A[1][1] = B[1][1]; A[2][2] = B[2][2];
+  solve6(A, bd);
+  double c[3] = {-bd[0], -bd[1], -bd[2]}, cs[3] = {-bd[3], -bd[4], -bd[5]};
+  double cl = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  double chk = c[0] * cs[0] + c[1] * cs[1] + c[2] * cs[2];
+  double angle = atan(cl);
+  double g[3] = {c[0] / cl, c[1] / cl, c[2] / cl};
+  double sa = sin(-angle / 2), b0 = cos(-angle / 2), b1 = g[0] * sa, b2 = g[1] * sa, b3 = g[2] * sa;
+  double R[3][3];
+  R[0][0] = b0 * b0 + b1 * b1 - b2 * b2 - b3 * b3; R[0][1] = 2 * (b1 * b2 + b0 * b3); R[0][2] = 2 * (b1 * b3 - b0 * b2);
+  R[1][0] = 2 * (b1 * b2 - b0 * b3); R[1][1] = b0 * b0 - b1 * b1 + b2 * b2 - b3 * b3; R[1][2] = 2 * (b2 * b3 + b0 * b1);
+  R[2][0] = 2 * (b1 * b3 + b0 * b2); R[2][1] = 2 * (b2 * b3 - b0 * b1); R[2][2] = b0 * b0 - b1 * b1 - b2 * b2 + b3 * b3;
+  double nn = b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[a][b] /= nn;
+  double skew = chk / (cl * cl);
+  double gs[3] = {(cs[0] - c[0] * skew) / cl, (cs[1] - c[1] * skew) / cl, (cs[2] - c[2] * skew) / cl};
+  double pt[3] = {g[1] * gs[2] - g[2] * gs[1], g[2] * gs[0] - g[0] * gs[2], g[0] * gs[1] - g[1] * gs[0]};
+  for (int k = 0; k < 16; ++k) M[k] = 0;
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) M[4 * b + a] = R[a][b];
+  for (int a = 0; a < 3; ++a)
+    M[12 + a] = -(R[a][0] * pt[0] + R[a][1] * pt[1] + R[a][2] * pt[2]) + g[a] * (skew * angle) + pt[a];
+  M[15] = 1;
+  return sqrt(sum / (double)n);
+}
+
 extern "C" {
 
 // ---- math pins
@@ -799,6 +845,7 @@ double orc_align(int algo, long n, const double* p1, const double* p2, const dou
     case 2: return align_svd(n, p1, p2, cm, cd, alignxf);
     case 3: return align_ortho(n, p1, p2, cm, cd, alignxf);
     case 4: return align_dual(n, p1, p2, alignxf);
+    case 5: return align_helix(n, p1, p2, alignxf);
     case 6: return align_apx(n, p1, p2, cm, cd, alignxf);
     case 10: return align_napx(n, p1, p2, nrm, cd, napx_weighted, alignxf);
   }

@@ -30,6 +30,7 @@
 #include "slam6d/icp6Dapx.h"
 #include "slam6d/icp6Dortho.h"
 #include "slam6d/icp6Ddual.h"
+#include "slam6d/icp6Dhelix.h"
 #include "slam6d/icp6Dnapx.h"
 #include "slam6d/normals.h"
 #include "slam6d/globals.icc"
@@ -56,6 +57,7 @@ icp6Dminimizer* make_minimizer(int algo) {
     case 2: return new icp6D_SVD(true);
     case 3: return new icp6D_ORTHO(true);
     case 4: return new icp6D_DUAL(true);
+    case 5: return new icp6D_HELIX(true);
     case 6: return new icp6D_APX(true);
     case 10: return new icp6D_NAPX(true);
     default: return nullptr;

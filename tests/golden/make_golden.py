@@ -65,14 +65,14 @@ def main():
     tree = L.ref_tree_create(P(model), len(model), 0, 20)
     for mode in (0, 2):
         n = len(data)
-        p1, p2, pn = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3))
+        p1, p2, pn = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
         sm, cm, cd = np.zeros(1), np.zeros(3), np.zeros(3)
         k = L.ref_get_pt_pairs(tree, P(S), P(data), P(nrm), 0, n, 0, 1, 400.0, mode, P(p1), P(p2), P(pn), P(sm),
                                P(cm), P(cd))
         out["pairs%d_p1" % mode], out["pairs%d_p2" % mode], out["pairs%d_n" % mode] = p1[:k], p2[:k], pn[:k]
         out["pairs%d_sum_cm_cd" % mode] = np.r_[sm, cm, cd]
         cmn, cdn = cm / k, cd / k
-        for algo in ((1, 2, 3, 4, 6) if mode == 0 else (1, 10)):
+        for algo in ((1, 2, 3, 4, 5, 6) if mode == 0 else (1, 10)):
             xf = np.zeros(16)
             rms = L.ref_align(algo, k, P(p1), P(p2), P(pn), P(cmn), P(cdn), P(xf))
             out["align_mode%d_algo%d" % (mode, algo)] = np.r_[xf, rms]
@@ -80,7 +80,7 @@ def main():
 
     # --- whole matches (harness loop around the reference's getPtPairs / Align / transform3)
     out["match_maxdist_iters_eps"] = np.array([20.0, 30, 1e-5])
-    for algo, mode in ((1, 0), (2, 0), (3, 0), (4, 0), (6, 0), (10, 2), (1, 2)):
+    for algo, mode in ((1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (10, 2), (1, 2)):
         r = orclib.ref_match(model, data, nrm if mode else None, algo=algo, mode=mode, max_dist=20.0,
                              max_iter=30, eps=1e-5)
         out["match_algo%d_mode%d_transmat" % (algo, mode)] = r["transmat"]

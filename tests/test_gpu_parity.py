@@ -112,7 +112,7 @@ def iteration_form(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3, 4, 6])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4, 5, 6])
 def test_match_point_to_point_vs_oracle(icp, ctx, algo, iteration_form):
     model, data, Ptrue = make_pair(icp, 60000, 50000)
     want = orclib.port_match(model, data, algo=algo, max_dist=25.0, max_iter=50, eps=1e-5)

@@ -65,7 +65,7 @@ def _pairs(rng, n, theta, pos, noise, scale=500.0):
     return np.ascontiguousarray(p1), np.ascontiguousarray(p2), np.ascontiguousarray(nr)
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3, 4, 6, 10])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4, 5, 6, 10])
 @pytest.mark.parametrize("n", [4, 50, 20000])
 def test_align_pairs_matches_oracle_align(icp, port, algo, n):
     rng = np.random.default_rng(100 * algo + n)

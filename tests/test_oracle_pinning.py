@@ -75,7 +75,7 @@ def test_golden_get_pt_pairs(mode):
     assert np.array_equal(np.r_[sm, cm, cd], GOLD["pairs%d_sum_cm_cd" % mode])
 
 
-@pytest.mark.parametrize("mode,algo", [(0, 1), (0, 2), (0, 3), (0, 4), (0, 6), (2, 1), (2, 10)])
+@pytest.mark.parametrize("mode,algo", [(0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (2, 1), (2, 10)])
 def test_golden_align(port, mode, algo):
     p1 = np.ascontiguousarray(GOLD["pairs%d_p1" % mode]); p2 = np.ascontiguousarray(GOLD["pairs%d_p2" % mode])
     pn = np.ascontiguousarray(GOLD["pairs%d_n" % mode])
@@ -89,7 +89,7 @@ def test_golden_align(port, mode, algo):
     assert orclib.rel_frobenius(xf, want[:16]) < 1e-12
 
 
-@pytest.mark.parametrize("algo,mode", [(1, 0), (2, 0), (3, 0), (4, 0), (6, 0), (10, 2), (1, 2)])
+@pytest.mark.parametrize("algo,mode", [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (10, 2), (1, 2)])
 def test_golden_match(algo, mode):
     md, it, eps = GOLD["match_maxdist_iters_eps"]
     r = orclib.port_match(GOLD["pair_model"], GOLD["pair_data"], GOLD["pair_data_normals"] if mode else None,
@@ -138,7 +138,7 @@ def test_live_math_helpers(port, ref):
         assert np.array_equal(c, d)
 
 
-@pytest.mark.parametrize("algo,mode", [(1, 0), (2, 0), (3, 0), (4, 0), (6, 0), (10, 2)])
+@pytest.mark.parametrize("algo,mode", [(1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (10, 2)])
 def test_live_match_vs_reference(ref, algo, mode):
     rng = np.random.default_rng(77 + algo)
     base = rng.uniform(-200, 200, (6000, 3)); base[:, 1] = np.abs(base[:, 1]) * 0.2
