@@ -120,3 +120,72 @@ def test_frames_file_format(icp, tmp_path):
     bad.add(0, np.full(16, np.nan), icp.FRAME_ICP)
     with pytest.raises(icp.B200ICPError):
         bad.save(0, p)
+
+
+# ---- differential test against a line-by-line restatement of readASCII / handle_line (src/scanio/helper.cc:577-835)
+def _ref_read_ascii(text):
+    """Python restatement (oracle side) of the reference's uos parsing rules.  Returns (points, ok)."""
+    pts, header = [], 10
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()                       # getline at EOF after a final newline reads an empty line: handled as success
+        trailing_empty = True
+    else:
+        trailing_empty = False
+    for raw in lines + ([""] if trailing_empty else []):
+        line = raw[:-1] if raw.endswith("\r") else raw
+        s = line.lstrip(" \t")
+        good, vals = True, []
+        if s != "" and not s.startswith("#"):
+            body = s.split("#", 1)[0]
+            toks = body.replace("\t", " ").split(" ")
+            toks = [t for t in toks if t != ""]
+            for t in toks:
+                try:
+                    if t.lower().lstrip("+-") in ("nan", "inf", "infinity") or t.lower().lstrip("+-").startswith("0x"):
+                        raise ValueError      # the generator below never emits these; keep the restatement simple
+                    vals.append(float(t))
+                except ValueError:
+                    good = False
+                    break
+            if good and len(vals) != 3:
+                good = False
+            if good:
+                pts.append(vals)
+        if not good:
+            header -= 1
+            if header < 0:
+                return None, False
+        elif header >= 0:
+            header = -1
+    return np.array(pts, dtype=np.float64).reshape(-1, 3), True
+
+
+def test_read_uos_differential_random_files(icp, tmp_path):
+    rng = np.random.default_rng(11)
+    pieces_good = [lambda: "%s %s %s" % tuple(repr(float(v)) for v in rng.normal(0, 100, 3)),
+                   lambda: "  %d\t%d   %d  " % tuple(rng.integers(-500, 500, 3)),
+                   lambda: "%.3e %.3e %.3e # c" % tuple(rng.normal(0, 1e3, 3)),
+                   lambda: "# only a comment", lambda: "", lambda: " \t "]
+    pieces_bad = [lambda: "1 2", lambda: "1 2 3 4", lambda: "a b c", lambda: "1 2 3x", lambda: "1,2,3", lambda: "--1 2 3"]
+    p = tmp_path / "r.3d"
+    outcomes = {True: 0, False: 0}
+    for trial in range(300):
+        n_head_bad = int(rng.choice([0, 0, 0, 1, 3, 10, 11]))
+        lines = [pieces_bad[rng.integers(len(pieces_bad))]() for _ in range(n_head_bad)]
+        for _ in range(int(rng.integers(0, 30))):
+            lines.append(pieces_good[rng.integers(len(pieces_good))]())
+        if rng.random() < 0.15 and lines:
+            lines.insert(int(rng.integers(0, len(lines) + 1)), pieces_bad[rng.integers(len(pieces_bad))]())
+        eol = "\r\n" if rng.random() < 0.3 else "\n"
+        text = eol.join(lines) + (eol if rng.random() < 0.7 else "")
+        _write(p, text)
+        want, ok = _ref_read_ascii(text)
+        outcomes[ok] += 1
+        if ok:
+            got = icp.read_uos(p)
+            assert got.shape == want.shape and np.array_equal(got, want), (trial, text)
+        else:
+            with pytest.raises(icp.B200ICPError):
+                icp.read_uos(p)
+    assert outcomes[True] > 100 and outcomes[False] > 10
