@@ -99,6 +99,7 @@ def _load():
         "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64), vp]),
         "b200icp_lum_graph_slam": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, C.POINTER(f64), C.POINTER(i32), vp]),
         "b200icp_matrix4_to_euler": (None, [dp, dp, dp]),
+        "b200icp_scan_calc_normals": (i32, [vp, vp, i32, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_reduce_octree_center": (i32, [vp, dp, sz, f64, dp, C.POINTER(sz)]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
@@ -267,6 +268,11 @@ class Scan:
         t = None if transmat is None else _f64(transmat).reshape(16)
         d = None if dalignxf is None else _f64(dalignxf).reshape(16)
         _check(lib.b200icp_scan_set_pose(self._h, _ptr(t), _ptr(d)))
+
+    def calc_normals(self, k, rpos):
+        """Scan::calcNormals on the resident scan (k-NN PCA, oriented towards rpos); no host round trip"""
+        r = _f64(rpos).reshape(3)
+        _check(lib.b200icp_scan_calc_normals(self.ctx._h, self._h, int(k), _ptr(r)))
 
     def transform(self, alignxf):
         """Scan::transform bookkeeping (scan.cc:851-898): pose matrices only, points stay where they are"""

@@ -976,6 +976,29 @@ int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, co
   return B200ICP_OK;
 }
 
+int b200icp_scan_calc_normals(b200icp_ctx* ctx, b200icp_scan* scan, int k, const double rPos[3]) {
+  if (!ctx || !scan || !rPos) return fail(B200ICP_EINVAL, "scan_calc_normals: NULL argument");
+  if (k < 1 || k > 32) return fail(B200ICP_EINVAL, "scan_calc_normals: k must be in [1, 32]");
+  CU_TRY(cudaSetDevice(ctx->device));
+  // normals live in the frame the grid was built in ("normal reduced" of the un-moved scan), like uploaded ones;
+  // the cumulative normal map (nmat) keeps applying on load
+  if (!scan->nrm.p || scan->nrm.count < scan->n) {
+    scan->nrm.stream = ctx->stream;
+    CU_TRY(scan->nrm.alloc(scan->n));
+    scan->g.nrm = scan->nrm.p;
+  }
+  const unsigned blocks = (unsigned)((scan->n + 127) / 128);
+  if (k <= 16)
+    normals_knn_kernel<16><<<blocks, 128, 0, ctx->stream>>>(scan->g, nullptr, k, rPos[0], rPos[1], rPos[2],
+                                                            reinterpret_cast<double*>(scan->nrm.p));
+  else
+    normals_knn_kernel<32><<<blocks, 128, 0, ctx->stream>>>(scan->g, nullptr, k, rPos[0], rPos[1], rPos[2],
+                                                            reinterpret_cast<double*>(scan->nrm.p));
+  CU_TRY(cudaGetLastError());
+  scan->has_normals = true;
+  return B200ICP_OK;
+}
+
 // ------------------------------------------------------------------------------------ LUM link
 namespace {
 bool gauss6(double A[6][6], double* b) {

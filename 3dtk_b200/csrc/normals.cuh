@@ -57,10 +57,12 @@ __device__ __forceinline__ void knn_scan_range(const GridDev& g, unsigned beg, u
   }
 }
 
+// out: 3 doubles per point in ORIGINAL row order (perm given), or -- perm == nullptr -- a double4 per point in the
+// scan's own cell-sorted order (written straight into the scan's "normal reduced" array)
 template <int K>
 __global__ void __launch_bounds__(128)
 normals_knn_kernel(GridDev g, const uint32_t* __restrict__ perm, int k, double rx, double ry, double rz,
-                   double* __restrict__ out /* original row order, 3 doubles */) {
+                   double* __restrict__ out) {
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j0 >= g.n) return;
   const double4 P = g.p64[j0];
@@ -132,8 +134,12 @@ normals_knn_kernel(GridDev g, const uint32_t* __restrict__ perm, int k, double r
   const double px = sx - rx, py = sy - ry, pz = sz - rz;
   if (n[0] * px + n[1] * py + n[2] * pz < 0.0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
   const double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-  const size_t dst = perm[j0];
-  out[3 * dst] = n[0] / nl; out[3 * dst + 1] = n[1] / nl; out[3 * dst + 2] = n[2] / nl;
+  if (perm) {
+    const size_t dst = perm[j0];
+    out[3 * dst] = n[0] / nl; out[3 * dst + 1] = n[1] / nl; out[3 * dst + 2] = n[2] / nl;
+  } else {
+    reinterpret_cast<double4*>(out)[j0] = make_double4(n[0] / nl, n[1] / nl, n[2] / nl, 0.0);
+  }
 }
 
 }  // namespace b200

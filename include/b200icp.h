@@ -279,6 +279,10 @@ int b200icp_frames_save(const b200icp_frames* frames, int scan, const char* path
  * flipped so that n . (p - rPos) >= 0, unit length.  Host pointers. */
 int b200icp_normals_knn(b200icp_ctx* ctx, const double* xyz, size_t n, int k, const double rPos[3],
                         double* normals_out);
+/* Scan::calcNormals on a scan that is already resident (src/slam6d/scan.cc:397-426): same kernel, same grid, the
+ * normals go straight into the scan's "normal reduced" array -- no host round trip, no second grid build.  rPos in
+ * the frame the scan was created in.  Replaces any normals the scan had. */
+int b200icp_scan_calc_normals(b200icp_ctx* ctx, b200icp_scan* scan, int k, const double rPos[3]);
 
 /* ---- octree reduction (the step immediately before the path) ----------------------
  * Replaces: Scan::calcReducedPoints + BOctTree + GetOctTreeCenter for `-r voxel_size -O 0`

@@ -266,3 +266,28 @@ def test_lum_link_vs_oracle(icp, ctx):
     np.testing.assert_allclose(CDg, CDw, rtol=1e-8, atol=1e-9 * np.abs(CDw).max())
     Cz, CDz, nz = icp.lum_link(ctx, first, icp.Scan(ctx, a), 100.0)   # identical clouds, moved model
     assert nz > 0
+
+
+def test_scan_calc_normals_on_device(icp, ctx):
+    """Scan::calcNormals on a resident scan == the host-pointer path, and a point-to-plane match fed by it == one fed
+    by uploaded normals (no host round trip, no second grid build)."""
+    model, data, _ = make_pair(icp, 40000, 30000, theta_deg=(0.3, -0.5, 0.4), pos=(6.0, -3.0, 2.0))
+    rpos = np.array([0.0, 150.0, 0.0])
+    want = icp.normals_knn(ctx, data, 10, rpos)
+    d1 = icp.Scan(ctx, data, max_dist_hint=25.0)
+    with pytest.raises(icp.B200ICPError):
+        d1.download(with_normals=True)                      # no normals yet
+    d1.calc_normals(10, rpos)
+    xyz, nrm = d1.download(with_normals=True)
+    assert np.array_equal(xyz, data)
+    np.testing.assert_allclose(nrm, want, rtol=0, atol=1e-12)
+    m = icp.Scan(ctx, model, max_dist_hint=25.0)
+    d2 = icp.Scan(ctx, data, normals=want, max_dist_hint=25.0)
+    eng = icp.icp6D(ctx, algo=icp.ALGO_NAPX, max_dist_match=25.0, max_num_iterations=30, epsilon_icp=1e-5)
+    r1 = eng.match(m, d1, icp.CLOSEST_PLANE_SIMPLE)
+    r2 = eng.match(m, d2, icp.CLOSEST_PLANE_SIMPLE)
+    assert r1["iterations"] == r2["iterations"] and np.array_equal(r1["npairs"], r2["npairs"])
+    assert orclib.rel_frobenius(d1.get_pose()[0], d2.get_pose()[0]) < 1e-10
+    d1.calc_normals(12, rpos)                               # replaces the normals in place
+    with pytest.raises(icp.B200ICPError):
+        d1.calc_normals(0, rpos)
