@@ -94,6 +94,7 @@ def _load():
         "b200icp_comm_destroy": (i32, [vp]),
         "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
+        "b200icp_lum_seed_cache": (i32, [vp, sz]),
         "b200icp_graph_from_poses": (i32, [dp, i32, f64, i32, dp, i32, C.POINTER(i32)]),
         "b200icp_lum_fill_gb": (i32, [vp, dp, i32, dp, i32, f64, dp, dp, dp]),
         "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64), vp]),
@@ -189,6 +190,10 @@ class Context:
 
     def set_stream(self, cuda_stream):
         _check(lib.b200icp_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def lum_seed_cache(self, limit_bytes):
+        """drop the remembered LUM link neighbours and set their memory limit (0 disables seeding)"""
+        _check(lib.b200icp_lum_seed_cache(self._h, int(limit_bytes)))
 
     def synchronize(self):
         _check(lib.b200icp_synchronize(self._h))

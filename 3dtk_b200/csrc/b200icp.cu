@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <map>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -86,6 +87,12 @@ constexpr int kMaxBlocksPerSm = 8;  // partial-sum workspace is sized sm_count *
 
 }  // namespace
 
+struct LinkKey {
+  const b200icp_scan* first;
+  const b200icp_scan* second;
+  bool operator<(const LinkKey& o) const { return first != o.first ? first < o.first : second < o.second; }
+};
+
 struct b200icp_ctx {
   int device = 0;
   int sm_count = 0;
@@ -97,6 +104,9 @@ struct b200icp_ctx {
   DevBuf<IterState> d_state;
   IterState* h_state = nullptr;     // pinned, 2 slots (speculative chunk polling)
   DevBuf<double> rms_log;
+  // neighbour caches of LUM links (first, second) -> int[second->n]: seeds for the link's next evaluation
+  std::map<LinkKey, DevBuf<int>> lum_seeds;
+  size_t lum_seed_bytes = 0, lum_seed_limit = (size_t)4 << 30;
   DevBuf<double> pose_log;          // [max_iter][16], see IterState::pose_log
   int pose_log_count = 0;           // iterations of the last match
   DevBuf<unsigned long long> npairs_log;
@@ -529,6 +539,14 @@ void b200icp_scan_destroy(b200icp_ctx* ctx, b200icp_scan* scan) {
   if (ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto it = ctx->lum_seeds.begin(); it != ctx->lum_seeds.end();) {   // seeds of links this scan was part of
+      if (it->first.first == scan || it->first.second == scan) {
+        ctx->lum_seed_bytes -= it->second.count * sizeof(int);
+        it = ctx->lum_seeds.erase(it);
+      } else {
+        ++it;
+      }
+    }
     scan->retarget(ctx->stream);   // buffers return to the stream-ordered pool through a stream that is alive
   } else {
     cudaDeviceSynchronize();       // no context left (e.g. interpreter teardown): the legacy stream is always valid
@@ -1022,6 +1040,16 @@ bool gauss6(double A[6][6], double* b) {
 }
 }  // namespace
 
+int b200icp_lum_seed_cache(b200icp_ctx* ctx, size_t limit_bytes) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->lum_seeds.clear();
+  ctx->lum_seed_bytes = 0;
+  ctx->lum_seed_limit = limit_bytes;
+  return B200ICP_OK;
+}
+
 int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
                      double max_dist_match2, double C[36], double CD[6], uint64_t* npairs) {
   if (!ctx || !first || !second || !C || !CD) return fail(B200ICP_EINVAL, "lum_link: NULL argument");
@@ -1031,7 +1059,35 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
   for (int i = 0; i < 36; ++i) C[i] = 0.0;
   for (int i = 0; i < 6; ++i) CD[i] = 0.0;
   if (npairs) *npairs = 0;
-  CU_TRY(ctx->nn_cache.ensure(second->n));
+  // per-link neighbour cache: the pairs of this link's previous evaluation seed the searches of this one (the graph
+  // relaxation evaluates every link once per iteration and the poses move little in between)
+  int* cache = nullptr;
+  int seeded = 0;
+  {
+    const LinkKey key{first, second};
+    auto it = ctx->lum_seeds.find(key);
+    if (it != ctx->lum_seeds.end() && it->second.count == second->n) {
+      cache = it->second.p;
+      seeded = 1;
+    } else if (ctx->lum_seed_limit > 0) {
+      const size_t need = second->n * sizeof(int);
+      if (ctx->lum_seed_bytes + need > ctx->lum_seed_limit) { ctx->lum_seeds.clear(); ctx->lum_seed_bytes = 0; }
+      if (need <= ctx->lum_seed_limit) {
+        DevBuf<int>& b = ctx->lum_seeds[key];
+        if (b.alloc(second->n) == cudaSuccess) {
+          cache = b.p;
+          ctx->lum_seed_bytes += need;
+        } else {
+          cudaGetLastError();
+          ctx->lum_seeds.erase(key);
+        }
+      }
+    }
+  }
+  if (!cache) {
+    CU_TRY(ctx->nn_cache.ensure(second->n));
+    cache = ctx->nn_cache.p;
+  }
   double* hx = ctx->h_small;   // pinned, 64 doubles
   memcpy(hx, second->dalignxf, 16 * sizeof(double));
   memcpy(hx + 16, first->dalignxf, 16 * sizeof(double));
@@ -1043,7 +1099,7 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
   const int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)(ctx->sm_count * 2));
   std::vector<double> hp((size_t)grid * 16);
   lum_link_kernel<1><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
-                                              ctx->nn_cache.p, ctx->partials.p);
+                                              cache, ctx->partials.p, seeded);
   CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());
@@ -1068,7 +1124,7 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
   memcpy(hx + 48, D, sizeof D);
   CU_TRY(cudaMemcpyAsync(ctx->d_small.p + 48, hx + 48, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
   lum_link_kernel<2><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
-                                              ctx->nn_cache.p, ctx->partials.p);
+                                              cache, ctx->partials.p, 0);
   CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());

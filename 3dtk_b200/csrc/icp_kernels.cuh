@@ -583,7 +583,7 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
 template <int PASS>
 __global__ void __launch_bounds__(kBlock, 2)
 lum_link_kernel(GridDev model, const double4* __restrict__ dq, uint32_t nd, const double* __restrict__ xfs,
-                double maxdist2, int* __restrict__ nn_cache, double* __restrict__ partials) {
+                double maxdist2, int* __restrict__ nn_cache, double* __restrict__ partials, int seeded) {
   __shared__ SearchSmemSmall sm;
   __shared__ double X[16], S[16], Sinv[16], D[6];
   const int tid = threadIdx.x;
@@ -610,7 +610,10 @@ lum_link_kernel(GridDev model, const double4* __restrict__ dq, uint32_t nd, cons
       double bd2;
       unsigned boidx;
       float unused_budget;
-      nn_warp_search<true>(model, sm, active, sx, sy, sz, maxdist2, -1, 0.f, bj, bd2, boidx, unused_budget, stage2);
+      // seeded: nn_cache holds this link's neighbours from the previous LUM iteration (an exact upper bound on the
+      // search radius; the result does not depend on it)
+      const int seed = (seeded && active) ? nn_cache[i] : -1;
+      nn_warp_search<true>(model, sm, active, sx, sy, sz, maxdist2, seed, 0.f, bj, bd2, boidx, unused_budget, stage2);
       if (active) nn_cache[i] = bj;
     } else if (active) {
       bj = nn_cache[i];

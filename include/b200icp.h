@@ -222,6 +222,11 @@ int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve
  * stays on the host (it is O(scans)). */
 int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
                      double max_dist_match2, double C[36], double CD[6], uint64_t* npairs);
+/* The context remembers, per (first, second) link, the neighbour found for every point of `second` and uses it to
+ * seed the link's next evaluation (the graph relaxation evaluates each link once per iteration while the poses
+ * barely move; a seed only bounds the search radius, the pairs do not depend on it).  This call drops all remembered
+ * links and sets the memory the context may spend on them (default 4 GiB; 0 disables seeding). */
+int b200icp_lum_seed_cache(b200icp_ctx* ctx, size_t limit_bytes);
 
 /* ---- LUM / graph back-end ----------------------------------------------------------------
  * Host-side loop around b200icp_lum_link; scans keep their pose in transMat / dalignxf, points are never moved.
