@@ -364,6 +364,9 @@ __device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict_
 #ifndef B200_DUAL_TILE
 #define B200_DUAL_TILE 0
 #endif
+#ifndef B200_TRIP_CHUNK
+#define B200_TRIP_CHUNK 1   // > 1: see the tile loop of icp_iter_kernel (experiment, default off)
+#endif
 #ifndef B200_ITER_MINBLOCKS
 #define B200_ITER_MINBLOCKS 3
 #endif
@@ -472,6 +475,20 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     const bool s1 = stream_one(i1, tile1 < ntiles && i1 < nd);
     enqueue(i0, s0);
     enqueue(i1, s1);
+  }
+#elif B200_TRIP_CHUNK > 1
+  // Untested experiment for the next round (profiles/r01_sched_cert_experiment.md, section 2): a warp's consecutive
+  // trips are kTripChunk NEIGHBOURING groups of 32 points instead of groups gridDim * 256 points apart, so a batch
+  // that the queue assembles from two trips still covers one region of the model.
+  {
+    constexpr uint32_t kTripChunk = B200_TRIP_CHUNK;
+    const uint32_t span = kBlock * kTripChunk;                     // points per block and stride
+    const uint32_t nspans = (nd + span - 1) / span;
+    for (uint32_t sp = blockIdx.x; sp < nspans; sp += gridDim.x)
+      for (uint32_t c = 0; c < kTripChunk; ++c) {
+        const uint32_t i = sp * span + (warp * kTripChunk + c) * 32u + lane;
+        enqueue(i, stream_one(i, i < nd));
+      }
   }
 #else
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
