@@ -189,3 +189,26 @@ def test_read_uos_differential_random_files(icp, tmp_path):
             with pytest.raises(icp.B200ICPError):
                 icp.read_uos(p)
     assert outcomes[True] > 100 and outcomes[False] > 10
+
+
+def test_read_uos_numbers_are_correctly_rounded(icp, tmp_path):
+    """the reader's fast decimal path (<= 15 digits, |exp10| <= 22) and its from_chars / strtod fallback must both
+    return what strtod returns -- Python's float() is a correctly rounded strtod"""
+    rng = np.random.default_rng(23)
+    toks = []
+    for fmt in ("%.6g", "%.3f", "%.10g", "%.15g", "%.17g", "%.8e", "%d", "%.1f", "%.12f"):
+        vals = np.concatenate([rng.normal(0, 1e3, 300), rng.normal(0, 1e-3, 100), rng.uniform(-1e15, 1e15, 100),
+                               10.0 ** rng.uniform(-25, 25, 100) * rng.choice([-1, 1], 100)])
+        toks += [fmt % (int(v) if fmt == "%d" else v) for v in vals]
+    toks += ["0", "-0", "0.0", "-0.000", "1e22", "1e23", "1e-22", "1e-23", "123456789012345", "1234567890123456",
+             "0.000000000000001", "9007199254740993", "4.35", "0.1", "2.675", "1.7976931348623157e308", "4.9e-324",
+             "5e-324", ".5", "5.", "-.25e1", "1E5", "1e+5", "1e-5", "00012.50", "+3.5"]
+    while len(toks) % 3:
+        toks.append("1")
+    p = tmp_path / "n.3d"
+    _write(p, "".join("%s %s %s\n" % tuple(toks[i:i + 3]) for i in range(0, len(toks), 3)))
+    got = icp.read_uos(p).reshape(-1)
+    want = np.array([float(t) for t in toks])
+    assert got.shape == want.shape
+    bad = [(t, g, w) for t, g, w in zip(toks, got, want) if not (g == w and np.signbit(g) == np.signbit(w))]
+    assert not bad, bad[:5]
