@@ -27,6 +27,19 @@ for th in cases:
     out_th, out_pos = np.zeros(3), np.zeros(3)
     L.ref_matrix4_to_euler(orclib.P(M), orclib.P(out_th), orclib.P(out_pos))
     mats.append(M); thetas.append(out_th); positions.append(out_pos)
+# LUM link (covarianceEuler): pairs by the compiled reference's KDtree / getPtPairs, sums restated in the harness with
+# the reference's newmat inverse (ref_lum_link; lum6Deuler.cc itself does not compile here).  Inputs are regenerated
+# from the seed by the test, only the outputs are stored.
+lrng = np.random.default_rng(12)
+base = lrng.uniform(-300, 300, (8000, 3)); base[:, 1] = np.abs(base[:, 1]) * 0.3
+lmodel = np.ascontiguousarray(base + lrng.normal(0, 0.3, base.shape))
+ldata = np.ascontiguousarray(base[:6000] + lrng.normal(0, 0.3, (6000, 3)) + [1.0, -0.5, 0.7])
+S = np.empty(16)
+L.ref_euler_to_matrix4(orclib.P(np.array([0.4, 0.2, -0.3])), orclib.P(np.deg2rad([0.1, -0.2, 0.15])), orclib.P(S))
+rt = L.ref_tree_create(orclib.P(lmodel), len(lmodel), 0, 20)
+linkC, linkCD = np.zeros(36), np.zeros(6)
+linkm = L.ref_lum_link(rt, orclib.P(S), orclib.P(ldata), len(ldata), 100.0, orclib.P(linkC), orclib.P(linkCD))
+L.ref_tree_free(rt)
 np.savez_compressed(os.path.join(HERE, "lum_vectors.npz"), m4=np.array(mats), theta=np.array(thetas),
-                    pos=np.array(positions))
+                    pos=np.array(positions), link_C=linkC, link_CD=linkCD, link_pairs=np.array([linkm]), link_S=S)
 print("wrote", len(mats), "Matrix4ToEuler vectors")

@@ -137,3 +137,35 @@ def test_graph_slam_errors(icp, ctx):
     assert e.value.code == -6
     with pytest.raises(icp.B200ICPError):
         lum.doGraphSlam6D(icp.Graph(np.array([[0, 5]], dtype=np.int32), 3), dev, 1)
+
+
+def _golden_link_inputs():
+    rng = np.random.default_rng(12)
+    base = rng.uniform(-300, 300, (8000, 3)); base[:, 1] = np.abs(base[:, 1]) * 0.3
+    model = np.ascontiguousarray(base + rng.normal(0, 0.3, base.shape))
+    data = np.ascontiguousarray(base[:6000] + rng.normal(0, 0.3, (6000, 3)) + [1.0, -0.5, 0.7])
+    return model, data
+
+
+def test_oracle_lum_link_matches_reference_golden():
+    """C / CD of one link against the stored output of the compiled reference's getPtPairs + newmat (works where
+    oracle/_ref is absent; the live variant is tests/test_oracle_pinning.py)"""
+    g = np.load(os.path.join(HERE, "golden", "lum_vectors.npz"))
+    model, data = _golden_link_inputs()
+    C, CD, m = orclib.port_lum_link(model, data, 100.0, g["link_S"])
+    assert m == int(g["link_pairs"][0]) and m > 1000
+    np.testing.assert_allclose(C.reshape(-1), g["link_C"], rtol=1e-9)
+    np.testing.assert_allclose(CD, g["link_CD"], rtol=1e-9, atol=1e-9 * np.abs(g["link_CD"]).max())
+
+
+@pytest.mark.gpu
+def test_gpu_lum_link_matches_reference_golden(icp, ctx):
+    g = np.load(os.path.join(HERE, "golden", "lum_vectors.npz"))
+    model, data = _golden_link_inputs()
+    first, second = icp.Scan(ctx, model, max_dist_hint=10.0), icp.Scan(ctx, data, max_dist_hint=10.0)
+    first.set_pose(None, g["link_S"])                      # Source->dalignxf
+    for _ in range(2):                                     # second evaluation runs seeded from the first: same result
+        C, CD, m = icp.lum_link(ctx, first, second, 100.0)
+        assert m == int(g["link_pairs"][0])
+        np.testing.assert_allclose(C.reshape(-1), g["link_C"], rtol=1e-9)
+        np.testing.assert_allclose(CD, g["link_CD"], rtol=1e-9, atol=1e-9 * np.abs(g["link_CD"]).max())
