@@ -81,6 +81,8 @@ def _load():
         "b200icp_frames_count": (i32, [vp, i32]),
         "b200icp_frames_get": (i32, [vp, i32, i32, dp, C.POINTER(i32)]),
         "b200icp_frames_save": (i32, [vp, i32, C.c_char_p, i32]),
+        "b200icp_frames_load": (i32, [vp, i32, C.c_char_p]),
+        "b200icp_graph_read_net": (i32, [C.c_char_p, dp, i32, C.POINTER(i32), C.POINTER(i32)]),
         "b200icp_scan_download": (i32, [vp, vp, dp, dp]),
         "b200icp_find_closest": (i32, [vp, vp, dp, f64, C.POINTER(C.c_int64)]),
         "b200icp_nn_batch": (i32, [vp, vp, dp, dp, sz, dp, f64, i32, dp, dp, dp]),
@@ -446,6 +448,10 @@ class Frames:
     def save(self, scan, path, append=False):
         _check(lib.b200icp_frames_save(self._h, scan, os.fsencode(path), 1 if append else 0))
 
+    def load(self, scan, path):
+        """BasicScan::readFrames: replaces the scan's frames by the file's"""
+        _check(lib.b200icp_frames_load(self._h, scan, os.fsencode(path)))
+
     def __del__(self):
         try:
             lib.b200icp_frames_destroy(self._h)
@@ -482,6 +488,15 @@ class Graph:
         _check(lib.b200icp_graph_from_poses(_ptr(rpos), rpos.shape[0], cldist2, loopsize, _ptr(links), n.value,
                                             C.byref(n)))
         return cls(links[:n.value], rpos.shape[0])
+
+    @classmethod
+    def from_net_file(cls, path):
+        """Graph(const string& netfile), graph.cc:52-74"""
+        n, ns = C.c_int(0), C.c_int(0)
+        _check(lib.b200icp_graph_read_net(os.fsencode(path), None, 0, C.byref(n), C.byref(ns)))
+        links = np.zeros((max(n.value, 1), 2), dtype=np.int32)
+        _check(lib.b200icp_graph_read_net(os.fsencode(path), _ptr(links), n.value, C.byref(n), C.byref(ns)))
+        return cls(links[:n.value], ns.value)
 
     def get_nr_links(self):
         return self.links.shape[0]

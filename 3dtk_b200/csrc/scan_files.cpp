@@ -291,6 +291,64 @@ int b200icp_frames_get(const b200icp_frames* f, int scan, int k, double transMat
   return B200ICP_OK;
 }
 
+int b200icp_frames_load(b200icp_frames* f, int scan, const char* path) {
+  // BasicScan::readFrames (basicScan.cc:872-900): the list is cleared first; empty lines and lines starting with
+  // '#' are skipped; every other line must hold 16 numbers and an unsigned type
+  if (!f || !path || scan < 0 || scan >= (int)f->scans.size())
+    return b200icp_set_error_(B200ICP_EINVAL, "frames_load: bad argument");
+  std::ifstream file(path);
+  if (!file) return b200icp_set_error_(B200ICP_EINVAL, (std::string("frames_load: cannot open ") + path).c_str());
+  std::vector<Frame> out;
+  std::string line;
+  while (std::getline(file, line)) {
+    if (line.length() == 0) continue;
+    if (line[0] == '#') continue;
+    std::istringstream ls(line);
+    Frame fr;
+    bool ok = true;
+    for (int i = 0; i < 16 && ok; ++i) ok = (bool)(ls >> fr.m[i]);
+    unsigned int type = 0;
+    if (ok) ok = (bool)(ls >> type);
+    if (!ok) return b200icp_set_error_(B200ICP_EINVAL, (std::string("Malformed line in ") + path + ": " + line).c_str());
+    fr.type = (int)type;
+    out.push_back(fr);
+  }
+  f->scans[(size_t)scan].swap(out);
+  return B200ICP_OK;
+}
+
+int b200icp_graph_read_net(const char* path, int* links, int cap, int* n_links, int* n_scans) {
+  // Graph::Graph(const std::string& netfile) (graph.cc:52-74): "<nrScans> <nrLinks>" then nrLinks pairs "from to";
+  // like there, the scan count reported is what Graph::addLink (graph.cc:157-174) counts -- ids not seen before
+  if (!path || !n_links) return b200icp_set_error_(B200ICP_EINVAL, "graph_read_net: NULL argument");
+  std::ifstream file(path);
+  if (!file) return b200icp_set_error_(B200ICP_EINVAL, (std::string("graph_read_net: cannot open ") + path).c_str());
+  int file_scans = 0, file_links = 0;
+  file >> file_scans >> file_links;
+  std::vector<int> from, to;
+  int nr_scans = 0;
+  for (int j = 0; j < file_links; ++j) {
+    if (!file.good()) return b200icp_set_error_(B200ICP_EINVAL, "Error while reading network structure");
+    int a = 0, b = 0;
+    file >> a >> b;
+    int present = 0;
+    for (size_t k = 0; k < from.size(); ++k) present += (from[k] == a) + (to[k] == a);
+    if (present == 0) ++nr_scans;
+    present = 0;
+    for (size_t k = 0; k < from.size(); ++k) present += (from[k] == b) + (to[k] == b);
+    if (present == 0) ++nr_scans;
+    from.push_back(a);
+    to.push_back(b);
+  }
+  *n_links = (int)from.size();
+  if (n_scans) *n_scans = nr_scans;
+  if (links) {
+    if ((int)from.size() > cap) return b200icp_set_error_(B200ICP_EINVAL, "graph_read_net: links array too small");
+    for (size_t k = 0; k < from.size(); ++k) { links[2 * k] = from[k]; links[2 * k + 1] = to[k]; }
+  }
+  return B200ICP_OK;
+}
+
 int b200icp_frames_save(const b200icp_frames* f, int scan, const char* path, int append) {
   if (!f || !path || scan < 0 || scan >= (int)f->scans.size())
     return b200icp_set_error_(B200ICP_EINVAL, "frames_save: bad argument");

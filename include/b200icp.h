@@ -277,6 +277,11 @@ int b200icp_frames_transform(b200icp_frames* frames, int scan, const double* tra
 int b200icp_frames_count(const b200icp_frames* frames, int scan);
 int b200icp_frames_get(const b200icp_frames* frames, int scan, int k, double transMat[16], int* type);
 int b200icp_frames_save(const b200icp_frames* frames, int scan, const char* path, int append);
+/* BasicScan::readFrames (basicScan.cc:872-900): replaces the scan's list by the file's frames */
+int b200icp_frames_load(b200icp_frames* frames, int scan, const char* path);
+/* Graph::Graph(const std::string& netfile) (src/slam6d/graph.cc:52-74): "<nrScans> <nrLinks>" then the links;
+ * *n_scans = the scan count Graph::addLink derives from the links (graph.cc:157-174).  links may be NULL to count. */
+int b200icp_graph_read_net(const char* path, int* links, int cap, int* n_links, int* n_scans);
 
 /* ---- normals --------------------------------------------------------------------------------
  * Replaces: calculateNormalsKNN + calculateNormal (src/slam6d/normals.cc:220-295, :518-558):

@@ -212,3 +212,46 @@ def test_read_uos_numbers_are_correctly_rounded(icp, tmp_path):
     assert got.shape == want.shape
     bad = [(t, g, w) for t, g, w in zip(toks, got, want) if not (g == w and np.signbit(g) == np.signbit(w))]
     assert not bad, bad[:5]
+
+
+def test_frames_load_round_trip_and_rules(icp, tmp_path):
+    fr = icp.Frames(2)
+    rng = np.random.default_rng(2)
+    mats = [rng.normal(0, 10, 16) for _ in range(5)]
+    for k, m in enumerate(mats):
+        fr.add(0, m, k % 5)
+    p = tmp_path / "scan000.frames"
+    fr.save(0, p)
+    back = icp.Frames(2)
+    back.add(1, mats[0], 1)                         # loading replaces the list (readFrames clears it)
+    back.load(1, p)
+    got = back.get(1)
+    assert [t for _, t in got] == [k % 5 for k in range(5)]
+    for (m, _), want in zip(got, mats):
+        np.testing.assert_allclose(m, want, rtol=1e-5)          # the file holds 6 significant digits
+    # empty lines and '#' lines are skipped, anything else malformed is an error (basicScan.cc:882-895)
+    _write(p, "# comment\n\n" + " ".join(["1"] * 16) + " 3\n")
+    back.load(1, p)
+    assert len(back.get(1)) == 1 and back.get(1)[0][1] == 3
+    _write(p, " ".join(["1"] * 15) + " x 3\n")
+    with pytest.raises(icp.B200ICPError):
+        back.load(1, p)
+    assert len(back.get(1)) == 1                                  # untouched by the failed load
+    with pytest.raises(icp.B200ICPError):
+        back.load(1, tmp_path / "missing.frames")
+
+
+def test_graph_net_file(icp, tmp_path):
+    p = tmp_path / "bremen.net"
+    _write(p, "4\n3\n0 1\n1 2\n3 4\n4 0\n")                        # the example of graph.cc:36-50: only 3 links are read
+    g = icp.Graph.from_net_file(p)
+    assert [tuple(l) for l in g.links] == [(0, 1), (1, 2), (3, 4)]
+    assert g.n_scans == 5                                         # what addLink counts: ids 0 1 2 3 4
+    _write(p, "13 4  0 1  1 2\n2 3 3 0")                          # any whitespace separates
+    g = icp.Graph.from_net_file(p)
+    assert [tuple(l) for l in g.links] == [(0, 1), (1, 2), (2, 3), (3, 0)] and g.n_scans == 4
+    _write(p, "3 5\n0 1\n1 2\n")                                  # promises more links than it holds
+    with pytest.raises(icp.B200ICPError):
+        icp.Graph.from_net_file(p)
+    with pytest.raises(icp.B200ICPError):
+        icp.Graph.from_net_file(tmp_path / "missing.net")
