@@ -73,6 +73,7 @@ def _load():
         "b200icp_last_poses": (i32, [vp, i32, dp]),
         "b200icp_read_uos": (i32, [C.c_char_p, C.POINTER(vp), C.POINTER(sz)]),
         "b200icp_read_pose": (i32, [C.c_char_p, dp, dp]),
+        "b200icp_write_uos": (i32, [C.c_char_p, dp, sz, f64, i32]),
         "b200icp_free": (None, [vp]),
         "b200icp_frames_create": (vp, [i32]),
         "b200icp_frames_destroy": (None, [vp]),
@@ -412,6 +413,12 @@ def read_uos(path):
         return out.reshape(-1, 3).copy()
     finally:
         lib.b200icp_free(p)
+
+
+def write_uos(path, xyz, scale=1.0, fmt=0):
+    """write_uos (scanio/writer.cc:146-178): fmt 0 "%lf", 1 high precision, 2 hex floats"""
+    xyz = _f64(xyz, 3)
+    _check(lib.b200icp_write_uos(os.fsencode(path), _ptr(xyz), xyz.shape[0], float(scale), int(fmt)))
 
 
 def read_pose(path):

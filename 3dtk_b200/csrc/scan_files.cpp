@@ -11,6 +11,7 @@
 // what remains on the host once the correspondence search is gone.
 #include "../../include/b200icp.h"
 
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -210,6 +211,45 @@ int b200icp_read_uos(const char* path, double** xyz_out, size_t* n_out) {
   *xyz_out = out;
   *n_out = total / 3;
   return B200ICP_OK;
+}
+
+int b200icp_write_uos(const char* path, const double* xyz, size_t n, double scale, int format) {
+  // write_uos(DataXYZ&, FILE*, scaleFac, hexfloat, high_precision) (src/scanio/writer.cc:146-178), the output of
+  // bin/scan_red: "%lf %lf %lf" (format 0), "%.016e" x3 (1, round-trips a double) or "%.013a" x3 (2, hex floats).
+  // Lines are formatted in parallel chunks and written in order.
+  if (!path || (!xyz && n) || format < 0 || format > 2) return b200icp_set_error_(B200ICP_EINVAL, "write_uos: bad argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) return b200icp_set_error_(B200ICP_EINVAL, (std::string("write_uos: cannot open ") + path).c_str());
+  static const char* const fmts[3] = {"%lf %lf %lf\n", "%.016e %.016e %.016e\n", "%.013a %.013a %.013a\n"};
+  const char* fmt = fmts[format];
+  unsigned nthr = std::thread::hardware_concurrency();
+  if (nthr == 0) nthr = 1;
+  if (nthr > 32) nthr = 32;
+  if (n < 50000) nthr = 1;
+  const size_t block = 1u << 16;                      // points per formatted piece
+  bool ok = true;
+  for (size_t base = 0; base < n && ok; base += block * nthr) {
+    std::vector<std::string> piece(nthr);
+    auto work = [&](unsigned t) {
+      const size_t lo = base + (size_t)t * block, hi = std::min(n, lo + block);
+      if (lo >= hi) return;
+      std::string& out = piece[t];
+      out.reserve((hi - lo) * 48);
+      char line[256];
+      for (size_t j = lo; j < hi; ++j) {
+        const int len = snprintf(line, sizeof line, fmt, scale * xyz[3 * j], scale * xyz[3 * j + 1], scale * xyz[3 * j + 2]);
+        if (len > 0) out.append(line, (size_t)std::min<int>(len, (int)sizeof line - 1));
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthr; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (unsigned t = 0; t < nthr && ok; ++t)
+      if (!piece[t].empty()) ok = fwrite(piece[t].data(), 1, piece[t].size(), f) == piece[t].size();
+  }
+  if (fclose(f) != 0) ok = false;
+  return ok ? B200ICP_OK : b200icp_set_error_(B200ICP_EINVAL, "write_uos: write failed");
 }
 
 int b200icp_read_pose(const char* path, double rPos[3], double rPosTheta[3]) {

@@ -269,6 +269,9 @@ enum { B200ICP_FRAME_INVALID = 0, B200ICP_FRAME_ICP = 1, B200ICP_FRAME_ICPINACTI
        B200ICP_FRAME_ELCH = 4 };   /* Scan::AlgoType, include/slam6d/scan.h:126 */
 int b200icp_read_uos(const char* path, double** xyz_out, size_t* n_out);
 int b200icp_read_pose(const char* path, double rPos[3], double rPosTheta[3]);
+/* write_uos (src/scanio/writer.cc:146-178; what bin/scan_red emits after the reduction): x y z per line times
+ * `scale`; format 0 = "%lf", 1 = "%.016e" (high precision), 2 = "%.013a" (hex floats, bit-exact). */
+int b200icp_write_uos(const char* path, const double* xyz, size_t n, double scale, int format);
 void b200icp_free(void* p);
 b200icp_frames* b200icp_frames_create(int n_scans);
 void b200icp_frames_destroy(b200icp_frames* frames);

@@ -255,3 +255,34 @@ def test_graph_net_file(icp, tmp_path):
         icp.Graph.from_net_file(p)
     with pytest.raises(icp.B200ICPError):
         icp.Graph.from_net_file(tmp_path / "missing.net")
+
+
+def test_write_uos_formats_and_round_trip(icp, tmp_path):
+    rng = np.random.default_rng(8)
+    pts = np.concatenate([rng.normal(0, 500, (70000, 3)), [[0.0, -0.0, 1e-300], [1e15, -1e-15, 123.456]]])
+    p = tmp_path / "scan000.3d"
+    icp.write_uos(p, pts, fmt=0)                       # "%lf %lf %lf": 6 decimals
+    first = open(p).readline()
+    assert first == "%f %f %f\n" % tuple(pts[0])
+    assert np.all(np.abs(icp.read_uos(p) - pts) <= 5.1e-7 + 1e-15 * np.abs(pts))
+    icp.write_uos(p, pts, fmt=1)                       # "%.016e": round-trips a double
+    assert open(p).readline() == "%.016e %.016e %.016e\n" % tuple(pts[0])
+    assert np.array_equal(icp.read_uos(p), pts)
+    icp.write_uos(p, pts, fmt=2)                       # "%.013a": hex floats, through the reader's strtod fallback
+    assert open(p).readline() == "%s %s %s\n" % tuple(_hex13(v) for v in pts[0])
+    back = icp.read_uos(p)
+    assert np.array_equal(back, pts) and np.array_equal(np.signbit(back), np.signbit(pts))
+    icp.write_uos(p, pts[:3], scale=100.0, fmt=1)      # scaleFac
+    assert np.array_equal(icp.read_uos(p), 100.0 * pts[:3])
+    icp.write_uos(p, np.zeros((0, 3)))
+    assert open(p).read() == ""
+    with pytest.raises(icp.B200ICPError):
+        icp.write_uos(tmp_path / "nodir" / "x.3d", pts[:1])
+
+
+def _hex13(v):
+    """C's %.013a for a double"""
+    import ctypes
+    buf = ctypes.create_string_buffer(64)
+    ctypes.CDLL(None).snprintf(buf, 64, b"%.013a", ctypes.c_double(float(v)))
+    return buf.value.decode()
