@@ -99,6 +99,7 @@ def _load():
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
         "b200icp_lum_seed_cache": (i32, [vp, sz]),
         "b200icp_graph_from_poses": (i32, [dp, i32, f64, i32, dp, i32, C.POINTER(i32)]),
+        "b200icp_graph_chain": (i32, [i32, i32, dp, i32, C.POINTER(i32)]),
         "b200icp_lum_fill_gb": (i32, [vp, dp, i32, dp, i32, f64, dp, dp, dp]),
         "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64), vp]),
         "b200icp_lum_graph_slam": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, C.POINTER(f64), C.POINTER(i32), vp]),
@@ -495,6 +496,15 @@ class Graph:
         _check(lib.b200icp_graph_from_poses(_ptr(rpos), rpos.shape[0], cldist2, loopsize, _ptr(links), n.value,
                                             C.byref(n)))
         return cls(links[:n.value], rpos.shape[0])
+
+    @classmethod
+    def chain(cls, n_scans, loop=False):
+        """Graph(int nScans, bool loop), graph.cc:76-105"""
+        n = C.c_int(0)
+        _check(lib.b200icp_graph_chain(n_scans, 1 if loop else 0, None, 0, C.byref(n)))
+        links = np.zeros((max(n.value, 1), 2), dtype=np.int32)
+        _check(lib.b200icp_graph_chain(n_scans, 1 if loop else 0, _ptr(links), n.value, C.byref(n)))
+        return cls(links[:n.value], n_scans)
 
     @classmethod
     def from_net_file(cls, path):

@@ -117,6 +117,20 @@ int b200icp_graph_from_poses(const double* rpos, int n_scans, double cldist2, in
   return B200ICP_OK;
 }
 
+int b200icp_graph_chain(int n_scans, int loop, int* links, int cap, int* n_links) {
+  // Graph::Graph(int nScans, bool loop), graph.cc:76-105: (i, i+1) for every scan, the last one back to 0 when `loop`
+  if (!n_links || n_scans < 0) return b200icp_set_error_(B200ICP_EINVAL, "graph_chain: bad argument");
+  const int nl = loop ? n_scans : (n_scans > 0 ? n_scans - 1 : 0);
+  *n_links = nl;
+  if (!links) return B200ICP_OK;
+  if (nl > cap) return b200icp_set_error_(B200ICP_EINVAL, "graph_chain: links array too small");
+  for (int i = 0; i < nl; ++i) {
+    links[2 * i] = i;
+    links[2 * i + 1] = loop ? (i != nl - 1 ? i + 1 : 0) : i + 1;
+  }
+  return B200ICP_OK;
+}
+
 int b200icp_lum_fill_gb(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
                         int n_links, double max_dist_match2, double* G, double* B, uint64_t* npairs_out) {
   if (!ctx || !scans || !links || !G || !B || n_scans < 2 || n_links < 0)

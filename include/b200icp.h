@@ -247,6 +247,8 @@ int b200icp_lum_seed_cache(b200icp_ctx* ctx, size_t limit_bytes);
  *   b200icp_matrix4_to_euler  Matrix4ToEuler (include/slam6d/globals.icc:540-578). */
 int b200icp_graph_from_poses(const double* rpos, int n_scans, double cldist2, int loopsize, int* links,
                              int cap, int* n_links);
+/* Graph::Graph(int nScans, bool loop) (src/slam6d/graph.cc:76-105): the minimally connected chain, optionally closed */
+int b200icp_graph_chain(int n_scans, int loop, int* links, int cap, int* n_links);
 int b200icp_lum_fill_gb(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
                         int n_links, double max_dist_match2, double* G, double* B, uint64_t* npairs_out);
 int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const double* G, const double* B,

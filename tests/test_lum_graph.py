@@ -56,6 +56,12 @@ def test_graph_from_poses(icp):
     assert icp.Graph.from_poses(rpos[:1], 1.0, 0).get_nr_links() == 0
 
 
+def test_graph_chain(icp):
+    assert [tuple(l) for l in icp.Graph.chain(4).links] == [(0, 1), (1, 2), (2, 3)]
+    assert [tuple(l) for l in icp.Graph.chain(4, loop=True).links] == [(0, 1), (1, 2), (2, 3), (3, 0)]
+    assert icp.Graph.chain(1).get_nr_links() == 0 and icp.Graph.chain(0).get_nr_links() == 0
+
+
 def _ring_scans(icp, n_scans, n_pts, noise_pos=2.0, noise_deg=0.3, seed=0):
     """n_scans resamplings of one scene, each displaced by a small pose error the relaxation has to remove.
     Returns (list of xyz in the global frame, transMat per scan)."""
