@@ -17,10 +17,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 extern "C" int b200icp_set_error_(int code, const char* msg);
@@ -122,29 +126,40 @@ int b200icp_read_uos(const char* path, double** xyz_out, size_t* n_out) {
   if (!path || !xyz_out || !n_out) return b200icp_set_error_(B200ICP_EINVAL, "read_uos: NULL argument");
   *xyz_out = nullptr;
   *n_out = 0;
-  FILE* f = fopen(path, "rb");
-  if (!f) return b200icp_set_error_(B200ICP_EINVAL, (std::string("read_uos: cannot open ") + path).c_str());
-  fseek(f, 0, SEEK_END);
-  const long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<char> buf((size_t)(sz > 0 ? sz : 0));
-  if (sz > 0 && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) {
-    fclose(f);
-    return b200icp_set_error_(B200ICP_EINVAL, "read_uos: short read");
+  // the file is mapped, not copied: the parser threads fault its pages in as they go
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return b200icp_set_error_(B200ICP_EINVAL, (std::string("read_uos: cannot open ") + path).c_str());
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+    close(fd);
+    return b200icp_set_error_(B200ICP_EINVAL, (std::string("read_uos: not a regular file: ") + path).c_str());
   }
-  fclose(f);
-  const char* base = buf.data();
-  const char* end = base + buf.size();
+  const size_t fsize = (size_t)sb.st_size;
+  struct Mapping {
+    void* p = nullptr; size_t n = 0;
+    ~Mapping() { if (p && p != MAP_FAILED) munmap(p, n); }
+  } map;
+  if (fsize > 0) {
+    map.p = mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    map.n = fsize;
+  }
+  close(fd);
+  if (fsize > 0 && map.p == MAP_FAILED) {
+    map.p = nullptr;
+    return b200icp_set_error_(B200ICP_EINVAL, "read_uos: mmap failed");
+  }
+  const char* base = fsize ? (const char*)map.p : "";
+  const char* end = base + fsize;
   // chunk boundaries on line starts
   unsigned nthr = std::thread::hardware_concurrency();
   if (nthr == 0) nthr = 1;
   if (nthr > 32) nthr = 32;
-  if (buf.size() < (1u << 20)) nthr = 1;
+  if (fsize < (1u << 20)) nthr = 1;
   std::vector<const char*> cut(nthr + 1);
   cut[0] = base;
   cut[nthr] = end;
   for (unsigned t = 1; t < nthr; ++t) {
-    const char* p = base + buf.size() / nthr * t;
+    const char* p = base + fsize / nthr * t;
     while (p < end && *p != '\n') ++p;
     cut[t] = p < end ? p + 1 : end;
     if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
