@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <cmath>
 #include <cstdio>
@@ -87,9 +88,11 @@ constexpr int kMaxBlocksPerSm = 8;  // partial-sum workspace is sized sm_count *
 
 }  // namespace
 
+// LUM seed cache key: the scans' ids (process-wide, monotonically increasing, never reused), not their addresses --
+// a scan allocated where a destroyed one lived can never pick up the old link's neighbours.
 struct LinkKey {
-  const b200icp_scan* first;
-  const b200icp_scan* second;
+  uint64_t first;
+  uint64_t second;
   bool operator<(const LinkKey& o) const { return first != o.first ? first < o.first : second < o.second; }
 };
 
@@ -134,7 +137,10 @@ struct b200icp_ctx {
   int blocks_per_sm_batch = 0;
 };
 
+static std::atomic<uint64_t> g_next_scan_id{1};
+
 struct b200icp_scan {
+  uint64_t id = g_next_scan_id.fetch_add(1);
   size_t n = 0;
   bool has_normals = false;
   GridDev g;                     // device pointers into the buffers below
@@ -540,7 +546,7 @@ void b200icp_scan_destroy(b200icp_ctx* ctx, b200icp_scan* scan) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto it = ctx->lum_seeds.begin(); it != ctx->lum_seeds.end();) {   // seeds of links this scan was part of
-      if (it->first.first == scan || it->first.second == scan) {
+      if (it->first.first == scan->id || it->first.second == scan->id) {
         ctx->lum_seed_bytes -= it->second.count * sizeof(int);
         it = ctx->lum_seeds.erase(it);
       } else {
@@ -617,8 +623,8 @@ int b200icp_metascan_create(b200icp_ctx* ctx, const b200icp_scan* const* scans, 
   CU_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   DevBuf<double> d_xyz, d_xf;
-  CU_TRY(d_xyz.alloc(3 * total));
-  CU_TRY(d_xf.alloc((size_t)25 * n_scans));
+  CU_TRY(d_xyz.alloc_async(3 * total, st));
+  CU_TRY(d_xf.alloc_async((size_t)25 * n_scans, st));
   std::vector<double> hx((size_t)25 * n_scans);
   for (int i = 0; i < n_scans; ++i) {
     memcpy(&hx[(size_t)25 * i], scans[i]->dalignxf, 16 * sizeof(double));
@@ -643,9 +649,9 @@ int b200icp_scan_download(b200icp_ctx* ctx, const b200icp_scan* scan, double* xy
   if (nrm_out && !scan->has_normals) return fail(B200ICP_ESTATE, "scan_download: scan has no normals");
   CU_TRY(cudaSetDevice(ctx->device));
   DevBuf<double> d_xyz, d_nrm, d_xf;
-  CU_TRY(d_xyz.alloc(3 * scan->n));
-  if (nrm_out) CU_TRY(d_nrm.alloc(3 * scan->n));
-  CU_TRY(d_xf.alloc(25));
+  CU_TRY(d_xyz.alloc_async(3 * scan->n, ctx->stream));
+  if (nrm_out) CU_TRY(d_nrm.alloc_async(3 * scan->n, ctx->stream));
+  CU_TRY(d_xf.alloc_async(25, ctx->stream));
   double hx[25];
   memcpy(hx, scan->dalignxf, 16 * sizeof(double));
   memcpy(hx + 16, scan->nmat, 9 * sizeof(double));
@@ -678,9 +684,9 @@ int b200icp_nn_batch_device(b200icp_ctx* ctx, const b200icp_scan* model, const d
   double id[16];
   m4_identity(id);
   const double* S = source_alignxf ? source_alignxf : id;
-  memcpy(ctx->h_small, S, 16 * sizeof(double));
-  m4_inverse(S, ctx->h_small + 16);
-  CU_TRY(cudaMemcpyAsync(ctx->d_small.p, ctx->h_small, 32 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BatchXf xfs;   // by value: no staging buffer shared with later calls (the device-pointer form returns unsynchronised)
+  memcpy(xfs.S, S, sizeof xfs.S);
+  m4_inverse(S, xfs.Sinv);
   if (ctx->blocks_per_sm_batch == 0) {
     int b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, nn_batch_kernel<false>, kBlock, 0);
@@ -690,10 +696,10 @@ int b200icp_nn_batch_device(b200icp_ctx* ctx, const b200icp_scan* model, const d
   const int grid = (int)std::min<size_t>(ntiles, (size_t)std::min(ctx->sm_count * ctx->blocks_per_sm_batch,
                                                                   max_iter_grid(ctx)));
   if (pairing_mode == B200ICP_CLOSEST_PLANE_SIMPLE)
-    nn_batch_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(model->g, d_q_xyz, d_q_nrm, n, ctx->d_small.p,
+    nn_batch_kernel<true><<<grid, kBlock, 0, ctx->stream>>>(model->g, d_q_xyz, d_q_nrm, n, xfs,
                                                             maxdist2, d_idx_out, d_d2_out, ctx->partials.p);
   else
-    nn_batch_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(model->g, d_q_xyz, d_q_nrm, n, ctx->d_small.p,
+    nn_batch_kernel<false><<<grid, kBlock, 0, ctx->stream>>>(model->g, d_q_xyz, d_q_nrm, n, xfs,
                                                              maxdist2, d_idx_out, d_d2_out, ctx->partials.p);
   CU_TRY(cudaGetLastError());
   if (sums_out) {
@@ -719,12 +725,13 @@ int b200icp_nn_batch(b200icp_ctx* ctx, const b200icp_scan* model, const double* 
   CU_TRY(cudaSetDevice(ctx->device));
   DevBuf<double> dq, dn, dd2;
   DevBuf<int32_t> didx;
-  CU_TRY(dq.alloc(3 * n));
-  CU_TRY(didx.alloc(n));
-  if (d2_out) CU_TRY(dd2.alloc(n));
+  // stream-ordered pool (release threshold raised in b200icp_create): no cudaMalloc / cudaFree per call
+  CU_TRY(dq.alloc_async(3 * n, ctx->stream));
+  CU_TRY(didx.alloc_async(n, ctx->stream));
+  if (d2_out) CU_TRY(dd2.alloc_async(n, ctx->stream));
   CU_TRY(cudaMemcpyAsync(dq.p, q_xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (q_nrm) {
-    CU_TRY(dn.alloc(3 * n));
+    CU_TRY(dn.alloc_async(3 * n, ctx->stream));
     CU_TRY(cudaMemcpyAsync(dn.p, q_nrm, 3 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   int rc = b200icp_nn_batch_device(ctx, model, dq.p, q_nrm ? dn.p : nullptr, n, source_alignxf, maxdist2,
@@ -1064,7 +1071,7 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
   int* cache = nullptr;
   int seeded = 0;
   {
-    const LinkKey key{first, second};
+    const LinkKey key{first->id, second->id};
     auto it = ctx->lum_seeds.find(key);
     if (it != ctx->lum_seeds.end() && it->second.count == second->n) {
       cache = it->second.p;

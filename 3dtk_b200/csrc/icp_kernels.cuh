@@ -535,16 +535,18 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
 }
 
 // ---- API path: SearchTree::getPtPairs over caller-supplied queries ---------------------------------
-// xf: [0..15] source_alignxf, [16..31] its inverse.  partials: [grid][8] = n, sum, cm[3], cd[3].
+// xfs: source_alignxf and its inverse, passed BY VALUE (kernel parameter space): a call never depends on a staging
+// buffer that a later call could overwrite before this one has run.  partials: [grid][8] = n, sum, cm[3], cd[3].
+struct BatchXf { double S[16], Sinv[16]; };
 template <bool PLANE>
 __global__ void __launch_bounds__(kBlock)
 nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* __restrict__ q_nrm,
-                size_t n, const double* __restrict__ xfs, double maxdist2, int32_t* __restrict__ idx_out,
+                size_t n, const __grid_constant__ BatchXf xfs, double maxdist2, int32_t* __restrict__ idx_out,
                 double* __restrict__ d2_out, double* __restrict__ partials) {
   __shared__ SearchSmemSmall sm;
   __shared__ double S[16], Sinv[16];
   const int tid = threadIdx.x;
-  if (tid < 16) { S[tid] = xfs[tid]; Sinv[tid] = xfs[16 + tid]; }
+  if (tid < 16) { S[tid] = xfs.S[tid]; Sinv[tid] = xfs.Sinv[tid]; }
   __syncthreads();
   double acc[8];
 #pragma unroll

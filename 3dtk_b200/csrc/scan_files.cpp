@@ -12,7 +12,10 @@
 #include "../../include/b200icp.h"
 
 #include <algorithm>
+#include <cerrno>
 #include <charconv>
+#include <clocale>
+#include <locale.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -40,9 +43,15 @@ bool parse_token(const char* b, const char* e, double* out) {
   if (*p == '+') ++p;
   auto r = std::from_chars(p, e, *out);
   if (r.ec == std::errc() && r.ptr == e) return true;
-  std::string tmp(b, e);       // rare spellings from_chars does not take (hex floats, "infinity", locale free)
+  // out of range (1e400, 1e-400): the reference's strtoval rejects the token when strtod sets ERANGE
+  // (helper.cc:242-271) -- "unable to parse line", not inf / 0
+  if (r.ec == std::errc::result_out_of_range) return false;
+  std::string tmp(b, e);       // rare spellings from_chars does not take (hex floats, "infinity")
   char* end = nullptr;
-  const double v = strtod(tmp.c_str(), &end);
+  errno = 0;
+  static const locale_t c_loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);   // the reference parses in the C locale
+  const double v = c_loc ? strtod_l(tmp.c_str(), &end, c_loc) : strtod(tmp.c_str(), &end);
+  if (errno == ERANGE) return false;
   if (end != tmp.c_str() + tmp.size()) return false;
   *out = v;
   return true;

@@ -13,7 +13,13 @@ fires).  Metric = data points searched per second = N_d * iterations / time.
   roofline   correspondence kernel: algorithmic bytes / mean launch time (CUDA events inside the library)
   cpu_baseline / --impl reference
              the reference's own CPU path (oracle/_ref: unmodified 3DTK kd.cc / searchTree.cc /
-             icp6Dquat.cc, OpenMP pICP arm, all host cores) on the same pair, bounded iterations
+             icp6Dquat.cc, OpenMP pICP arm, all host cores) on the SAME pair and the SAME match (all iterations
+             to the reference's convergence test); the sample is bounded by the number of matches (<= 2), not
+             by the iterations.  The reference arm never loads the product library: its inputs come from
+             oracle/_build/libscenegen.so (same generator source, bit-identical arrays).
+  parity     (GPU line) the final pose and the pair count of every iteration against a live run of the compiled
+             reference on the identical arrays (serial-arm arithmetic, neighbour search spread over the host
+             cores: oracle/ref_harness.cc) -- the BASELINE.md section 3 gate (< 1e-4 relative Frobenius).
 
 Multi-GPU (--gpus N under torchrun): the path shards by scan pair -- every rank matches its own pair,
 no data-path collective ("scaling": "weak"); time = max over ranks.
@@ -50,7 +56,8 @@ def parse():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--exact", type=int, default=1)
     ap.add_argument("--max-iter", type=int, default=50)
-    ap.add_argument("--cpu-iters", type=int, default=4, help="iterations of the CPU baseline sample")
+    ap.add_argument("--ref-matches", type=int, default=2, help="upper bound of timed matches of the reference arm")
+    ap.add_argument("--no-parity", action="store_true", help="skip the live parity check against oracle/_ref")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cell-edge", type=float, default=0.0)
     ap.add_argument("--shard", default="pairs", choices=["pairs", "queries"],
@@ -68,6 +75,24 @@ def make_pair(icp, n, rank):
     Pm = icp.euler_to_matrix4(np.array(POSE_POS), np.deg2rad(np.array(POSE_THETA_DEG)))
     Pinv, _ = icp.m4inv(Pm)
     return model, icp.transform_points(Pinv, data), Pm
+
+
+def make_pair_standalone(n, rank):
+    """The same pair (bit-identical arrays) from oracle/_build/libscenegen.so -- for the reference arm, which must
+    not load the product library."""
+    so = os.path.join(ROOT, "oracle", "_build", "libscenegen.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+    L = C.CDLL(so)
+    L.scenegen_pair.restype = C.c_int
+    L.scenegen_pair.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_double] + [C.c_void_p] * 5
+    model, data, P = np.empty((n, 3)), np.empty((n, 3)), np.empty(16)
+    pos, th = np.array(POSE_POS), np.array(POSE_THETA_DEG)
+    rc = L.scenegen_pair(7, 42 + 2 * rank, 43 + 2 * rank, n, 0.5, pos.ctypes.data, th.ctypes.data,
+                         model.ctypes.data, data.ctypes.data, P.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("scenegen_pair failed: %d" % rc)
+    return model, data, P
 
 
 class ClockSampler:
@@ -183,45 +208,55 @@ def ncu_traffic():
         return None, None
 
 
-def cpu_reference_run(model, data, max_iter, steps, warmup):
-    """The reference's OpenMP pICP arm (icp6D.cc:129-222) from oracle/_ref on all host cores."""
-    import orclib
-    from orclib import P
-    L = orclib.ref(omp=True)
-    kind = "reference"
-    if L is None:
-        return None
+def host_threads():
     # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1); the harness passes
     # the count in an explicit num_threads clause
     try:
         threads = len(os.sched_getaffinity(0))
     except Exception:
         threads = os.cpu_count() or 1
-    threads = max(1, min(threads, 256))
+    return max(1, min(threads, 256))
+
+
+def cpu_reference_run(model, data, max_iter, matches, serial_semantics=False):
+    """`matches` full matches of the compiled reference (oracle/_ref) on all host cores.
+    serial_semantics=False: the reference's OpenMP pICP arm (icp6D.cc:129-222: getPtPairsParallel + Align_Parallel).
+    serial_semantics=True : the serial arm's arithmetic (icp6D.cc:224-244) with the k-d tree searches spread over
+                            the cores -- bit-identical to the serial reference, used as the parity oracle."""
+    import orclib
+    from orclib import P
+    L = orclib.ref(omp=True)
+    if L is None:
+        return None
+    threads = host_threads()
     m = np.ascontiguousarray(model)
     t0 = time.perf_counter()
     tree = L.ref_tree_create(P(m), len(m), 0, 20)
     build_s = time.perf_counter() - t0
-    times, iters = [], []
-    for s in range(warmup + steps):
+    times, iters, last = [], [], None
+    for s_ in range(matches):
         d = np.ascontiguousarray(data).copy()
         T, D, S = orclib.identity(), orclib.identity(), orclib.identity()
         rms = np.zeros(max_iter); npairs = np.zeros(max_iter, dtype=np.int64)
         done, ms = C.c_int(0), C.c_double(0)
         t0 = time.perf_counter()
-        L.ref_match(tree, P(S), P(d), None, len(d), P(T), P(D), 1, 0, 25.0, max_iter, 1e-5, 1, threads,
-                    P(rms), P(npairs), C.byref(done), C.byref(ms))
+        ret = L.ref_match(tree, P(S), P(d), None, len(d), P(T), P(D), 1, 0, 25.0, max_iter, 1e-5, 1,
+                          -threads if serial_semantics else threads,
+                          P(rms), P(npairs), C.byref(done), C.byref(ms))
         dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt); iters.append(done.value)
+        times.append(dt); iters.append(done.value)
+        last = {"transmat": T.copy(), "npairs": npairs[:done.value].copy(), "rms": rms[:done.value].copy(),
+                "iterations": ret, "iterations_run": done.value}
     L.ref_tree_free(tree)
     total_t, total_it = sum(times), sum(iters)
-    return {"value": len(data) * total_it / total_t, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": "full %d x %d pair, icp6D_QUAT OpenMP arm, first %d iterations per match, %d matches; "
-                      "k-d tree build (%.2f s) excluded as the reference does (icp6D.cc:127)"
-                      % (len(model), len(data), max_iter, steps, build_s),
+    arm = ("serial-arm arithmetic (Scan::getPtPairs + icp6D_QUAT::Align), k-d tree searches on %d threads" % threads
+           if serial_semantics else "icp6D_QUAT OpenMP pICP arm (getPtPairsParallel + Align_Parallel)")
+    return {"value": len(data) * total_it / total_t, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "full %d x %d pair, %s, %d full match(es) of %d iterations each (all iterations to the "
+                      "reference's convergence test); k-d tree build (%.2f s) excluded as the reference does "
+                      "(icp6D.cc:127)" % (len(model), len(data), arm, matches, iters[-1], build_s),
             "iters_per_sec": total_it / total_t, "ms_per_step": 1e3 * total_t / max(len(times), 1),
-            "iterations": total_it}
+            "iterations": total_it, "matches": matches, "last": last}
 
 
 def main():
@@ -235,13 +270,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:   # by path: the package __init__ raises while the library is still missing
-        spec = importlib.util.spec_from_file_location(
-            "_b200icp_build", os.path.join(os.path.dirname(os.path.abspath(__file__)), "3dtk_b200", "build.py"))
-        build = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(build)
-        build.build()
-    icp = importlib.import_module("3dtk_b200")
+    if a.impl != "reference":
+        if rank == 0:   # by path: the package __init__ raises while the library is still missing
+            spec = importlib.util.spec_from_file_location(
+                "_b200icp_build", os.path.join(os.path.dirname(os.path.abspath(__file__)), "3dtk_b200", "build.py"))
+            build = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(build)
+            build.build()
+        icp = importlib.import_module("3dtk_b200")
 
     config = {"workload": "synthetic 2-scan pair (BASELINE configs[1]): %d pts each, known SE(3) offset, "
                           "point-to-point icp6D_QUAT, d=25 i=%d epsICP=1e-5" % (a.points, a.max_iter),
@@ -257,16 +293,20 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        model, data, _ = make_pair(icp, a.points, 0)
-        r = cpu_reference_run(model, data, a.cpu_iters, a.steps, a.warmup)
+        model, data, _ = make_pair_standalone(a.points, 0)
+        matches = max(1, min(a.steps, a.ref_matches))
+        r = cpu_reference_run(model, data, a.max_iter, matches)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref3dtk_omp.so not built"}))
             return 0
-        config["max_iter"] = a.cpu_iters
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "iters_per_sec": r["iters_per_sec"],
+                "iterations_per_match": r["iterations"] / r["matches"], "matches_timed": r["matches"],
+                "note": "one step = one full match (same config as the GPU arm); the run is bounded to %d timed "
+                        "match(es) and no warm-up matches (CPU code; the k-d tree is built once, outside the "
+                        "timed region, as the reference's own timer does)" % r["matches"],
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -453,9 +493,31 @@ def main():
                     "d2h_bytes_per_step": 2 * 640 * max(1, (a.max_iter + 3) // 4) + 16 * a.max_iter,
                     "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches, "roofline": roofline}
+    line["timing_note"] = ("value / e2e count every iteration of the match incl. iteration 0 (the reference's own "
+                           "timer starts at iteration 1, icp6D.cc:127); grid build is outside `value`, inside `e2e`")
+    if world == 1 and not a.no_parity:
+        # ---- BASELINE.md section 3 gate at the bench size: same arrays through the compiled reference
+        try:
+            pr = cpu_reference_run(model, data, a.max_iter, 1, serial_semantics=True)
+        except Exception as ex:
+            pr = None
+            line["parity_error"] = repr(ex)
+        if pr:
+            import orclib
+            ref_T = pr["last"]["transmat"]
+            got_np = np.asarray(last["npairs"], dtype=np.int64)
+            line["pose_rel_frobenius_vs_reference"] = float(orclib.rel_frobenius(T_final, ref_T))
+            line["npairs_per_iteration_equal"] = bool(len(got_np) == len(pr["last"]["npairs"]) and
+                                                      np.array_equal(got_np, pr["last"]["npairs"]))
+            line["iterations_equal"] = bool(last["iterations"] == pr["last"]["iterations"])
+            line["parity"] = {"oracle": "oracle/_ref (compiled 3DTK kd.cc / searchTree.cc / icp6Dquat.cc), " + pr["sample"],
+                              "gate": "pose_rel_frobenius_vs_reference < 1e-4 (BASELINE.md section 3)",
+                              "passed": bool(line["pose_rel_frobenius_vs_reference"] < 1e-4),
+                              "reference_iterations": int(pr["last"]["iterations_run"]),
+                              "reference_seconds": pr["ms_per_step"] * 1e-3}
     if world == 1 and not a.no_cpu_baseline:
         try:
-            cb = cpu_reference_run(model, data, a.cpu_iters, 1, 0)
+            cb = cpu_reference_run(model, data, a.max_iter, 1)
         except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
             cb = None
             line["cpu_baseline_error"] = repr(ex)

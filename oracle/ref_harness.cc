@@ -215,7 +215,9 @@ void ref_matrix4_to_euler(const double* m, double* theta, double* pos) {
 // Scan::transformReduced does; `data_transmat` / `data_dalignxf` play Scan::transMat /
 // Scan::dalignxf of the *data* scan; `model_dalignxf` is Source->dalignxf (scan.cc:1240).
 // parallel_threads == 0 -> serial arm (icp6D.cc:224-244, the parity oracle);
-// parallel_threads  > 0 -> OpenMP arm (icp6D.cc:129-222) with that many threads.
+// parallel_threads  > 0 -> OpenMP arm (icp6D.cc:129-222) with that many threads;
+// parallel_threads  < 0 -> the serial arm's arithmetic with the neighbour search spread over -parallel_threads threads
+//                          (OpenMP build only): bit-identical to the serial arm, for full-size parity checks.
 // Returns the value `match` returns (the loop index at exit); rms_out/npairs_out get one entry
 // per executed iteration, *iters_done their count.
 int ref_match(void* model_tree, const double* model_dalignxf, double* data_xyz, double* data_nrm,
@@ -308,6 +310,40 @@ int ref_match(void* model_tree, const double* model_dalignxf, double* data_xyz, 
       // serial arm: Scan::getPtPairs (scan.cc:1220-1260) + Align
       double centroid_m[3] = {0, 0, 0}, centroid_d[3] = {0, 0, 0};
       std::vector<PtPair> pairs;
+#ifdef _OPENMP
+      if (parallel_threads < 0 && rnd <= 1) {
+        // SERIAL SEMANTICS, PARALLEL SEARCH (parity oracle for full-size pairs): the reference's getPtPairs runs
+        // on contiguous chunks of the data scan in -parallel_threads threads; the chunks' pair vectors are then
+        // concatenated in chunk order -- the order the serial loop produces -- and the running sums of
+        // getPtPairs (searchTree.cc:164-177) are re-taken over that list in order, so `pairs`, `centroid_*` and
+        // `ret` hold bit for bit what one serial getPtPairs call leaves; Align below is the serial one.
+        const int T = std::min(-parallel_threads, (int)MAX_OPENMP_NUM_THREADS);
+        const long step = (nd + T - 1) / T;
+        std::vector<std::vector<PtPair> > part(T);
+#pragma omp parallel num_threads(T)
+        {
+          const int tn = omp_get_thread_num();
+          long lo = std::min((long)tn * step, nd), hi = std::min(lo + step, nd);
+          double sum_t = 0.0, cm_t[3] = {0, 0, 0}, cd_t[3] = {0, 0, 0};
+          t->tree->getPtPairs(&part[tn], src_xf, xyz_r, nrm_r, (unsigned)lo, (unsigned)hi, tn, rnd,
+                              max_dist_match2, sum_t, cm_t, cd_t, (PairingMode)pairing_mode);
+        }
+        size_t total = 0;
+        for (int i = 0; i < T; ++i) total += part[i].size();
+        pairs.reserve(total);
+        for (int i = 0; i < T; ++i) {
+          pairs.insert(pairs.end(), part[i].begin(), part[i].end());
+          std::vector<PtPair>().swap(part[i]);
+        }
+        for (size_t i = 0; i < pairs.size(); ++i) {
+          const PtPair& pr = pairs[i];
+          centroid_m[0] += pr.p1.x; centroid_m[1] += pr.p1.y; centroid_m[2] += pr.p1.z;
+          centroid_d[0] += pr.p2.x; centroid_d[1] += pr.p2.y; centroid_d[2] += pr.p2.z;
+          double p12[3] = {pr.p1.x - pr.p2.x, pr.p1.y - pr.p2.y, pr.p1.z - pr.p2.z};
+          ret += Len2(p12);
+        }
+      } else
+#endif
       t->tree->getPtPairs(&pairs, src_xf, xyz_r, nrm_r, 0u, (unsigned)nd, 0, rnd, max_dist_match2,
                           ret, centroid_m, centroid_d, (PairingMode)pairing_mode);
       size_t sz = pairs.size();

@@ -3,6 +3,8 @@
 Bars: NN indices / found flags / pair counts bit-exact (index work); distances bit-exact in exact mode;
 transforms of whole matches within 1e-4 relative Frobenius (north_star), in practice ~1e-9.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -235,6 +237,31 @@ def test_full_size_properties(icp, ctx, iteration_form):
     tree = orclib.PortTree(model)
     wi, wd = tree.find_closest_batch(q, 625.0)
     assert np.array_equal(idx >= 0, wi >= 0) and np.array_equal(d2[wi >= 0], wd[wi >= 0])
+
+
+def test_bench_config_parity_vs_compiled_reference(icp, ctx):
+    """BASELINE.md section 3 gate at the bench size (configs[1], 1M x 1M, icp6D_QUAT): the fused match against the
+    compiled, unmodified reference (oracle/_ref: kd.cc / searchTree.cc / icp6Dquat.cc) run on the identical arrays
+    with the serial arm's arithmetic (icp6D.cc:224-244), its k-d tree searches spread over the host cores
+    (oracle/ref_harness.cc, bit-identical to the serial arm: tests/test_oracle_pinning.py)."""
+    if orclib.ref(omp=True) is None:
+        pytest.skip("oracle/_ref/libref3dtk_omp.so not built (needs /root/reference)")
+    n = 1_000_000
+    model, data, _ = make_pair(icp, n, n)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except Exception:
+        threads = os.cpu_count() or 1
+    want = orclib.ref_match(model, data, algo=1, max_dist=25.0, max_iter=50, eps=1e-5, threads=-min(threads, 256),
+                            omp=True)
+    m, d = icp.Scan(ctx, model, max_dist_hint=25.0), icp.Scan(ctx, data, max_dist_hint=25.0)
+    got = icp.icp6D(ctx, algo=1, max_dist_match=25.0, max_num_iterations=50, epsilon_icp=1e-5).match(m, d)
+    T, _ = d.get_pose()
+    assert got["iterations"] == want["iterations"]
+    assert np.array_equal(got["npairs"], want["npairs"])           # same pair count in every iteration
+    np.testing.assert_allclose(got["rms"], want["rms"], rtol=1e-9)
+    err = orclib.rel_frobenius(T, want["transmat"])
+    assert err < 1e-8 < TOL_MATCH, err                             # north-star gate: 1e-4
 
 
 def test_normals_knn_vs_oracle(icp, ctx, port):

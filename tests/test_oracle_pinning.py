@@ -189,3 +189,20 @@ def test_live_lum_link_vs_harness_with_reference_newmat(port, ref):
     # identical clouds -> zero information (lum6Deuler.cc:219-231)
     C3, D3, m3 = orclib.port_lum_link(model, model, 100.0)
     assert m3 == len(model) and not C3.any() and not D3.any()
+
+
+def test_parallel_search_serial_align_arm_is_bit_identical_to_the_serial_reference():
+    """ref_match(parallel_threads < 0) -- the full-size parity oracle of bench.py and tests/test_gpu_parity.py --
+    must leave exactly what the serial arm (icp6D.cc:224-244) leaves: same pairs in the same order, same sums."""
+    import importlib
+    if orclib.ref(omp=True) is None:
+        pytest.skip("oracle/_ref/libref3dtk_omp.so not built (needs /root/reference)")
+    icp = importlib.import_module("3dtk_b200")
+    from conftest import make_pair
+    model, data, _ = make_pair(icp, 30000, 25001)
+    a = orclib.ref_match(model, data, algo=1, threads=0, omp=False)     # serial library, serial arm
+    for th in (-3, -8):
+        b = orclib.ref_match(model, data, algo=1, threads=th, omp=True)
+        assert a["iterations"] == b["iterations"]
+        assert np.array_equal(a["npairs"], b["npairs"]) and np.array_equal(a["rms"], b["rms"])
+        assert np.array_equal(a["transmat"], b["transmat"]) and np.array_equal(a["xyz"], b["xyz"])

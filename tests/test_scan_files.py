@@ -38,7 +38,9 @@ def test_read_uos_header_rule(icp, tmp_path):
     with pytest.raises(icp.B200ICPError):
         icp.read_uos(p)
     # once a line has been handled (a point, but also a comment or an empty line) every bad line is fatal
-    for text in ("1 2 3\nbad\n", "# c\nbad\n1 2 3\n", "1 2 3\n1 2\n", "1 2 3\n1 2 3 4\n", "1 2 3\n1 2 x3\n"):
+    # ... including out-of-range tokens: strtoval rejects what strtod flags with ERANGE (helper.cc:242-271)
+    for text in ("1 2 3\nbad\n", "# c\nbad\n1 2 3\n", "1 2 3\n1 2\n", "1 2 3\n1 2 3 4\n", "1 2 3\n1 2 x3\n",
+                 "1 2 3\n1e400 2 3\n", "1 2 3\n1 -1e400 3\n", "1 2 3\n1 2 1e-400\n"):
         _write(p, text)
         with pytest.raises(icp.B200ICPError):
             icp.read_uos(p)
