@@ -97,6 +97,7 @@ def _load():
         "b200icp_comm_destroy": (i32, [vp]),
         "b200icp_last_profile": (i32, [vp, i32, dp, dp, dp, dp]),
         "b200icp_lum_link": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
+        "b200icp_lum_link_quat": (i32, [vp, vp, vp, f64, dp, dp, C.POINTER(C.c_uint64)]),
         "b200icp_lum_seed_cache": (i32, [vp, sz]),
         "b200icp_graph_from_poses": (i32, [dp, i32, f64, i32, dp, i32, C.POINTER(i32)]),
         "b200icp_graph_chain": (i32, [i32, i32, dp, i32, C.POINTER(i32)]),
@@ -400,6 +401,13 @@ def lum_link(ctx, first, second, max_dist_match2):
     Cm, CD, n = np.zeros(36), np.zeros(6), C.c_uint64(0)
     _check(lib.b200icp_lum_link(ctx._h, first._h, second._h, max_dist_match2, _ptr(Cm), _ptr(CD), C.byref(n)))
     return Cm.reshape(6, 6), CD, n.value
+
+
+def lum_link_quat(ctx, first, second, max_dist_match2):
+    """lum6DQuat::covarianceQuat for one graph link -> (C[7,7], CD[7], npairs)"""
+    Cm, CD, n = np.zeros(49), np.zeros(7), C.c_uint64(0)
+    _check(lib.b200icp_lum_link_quat(ctx._h, first._h, second._h, max_dist_match2, _ptr(Cm), _ptr(CD), C.byref(n)))
+    return Cm.reshape(7, 7), CD, n.value
 
 
 FRAME_INVALID, FRAME_ICP, FRAME_ICPINACTIVE, FRAME_LUM, FRAME_ELCH = 0, 1, 2, 3, 4   # Scan::AlgoType

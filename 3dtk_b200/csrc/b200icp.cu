@@ -1025,46 +1025,41 @@ int b200icp_scan_calc_normals(b200icp_ctx* ctx, b200icp_scan* scan, int k, const
 }
 
 // ------------------------------------------------------------------------------------ LUM link
+extern "C++" {
 namespace {
-bool gauss6(double A[6][6], double* b) {
-  for (int c = 0; c < 6; ++c) {
+// Gaussian elimination with partial pivoting, N <= 7 (the reference inverts MM with newmat's .i())
+template <int N>
+bool gauss_solve(double (&A)[N][N], double* b) {
+  for (int c = 0; c < N; ++c) {
     int piv = c;
-    for (int r = c + 1; r < 6; ++r) if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
+    for (int r = c + 1; r < N; ++r) if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
     if (A[piv][c] == 0.0) return false;
-    if (piv != c) { for (int k = 0; k < 6; ++k) std::swap(A[c][k], A[piv][k]); std::swap(b[c], b[piv]); }
-    for (int r = c + 1; r < 6; ++r) {
+    if (piv != c) { for (int k = 0; k < N; ++k) std::swap(A[c][k], A[piv][k]); std::swap(b[c], b[piv]); }
+    for (int r = c + 1; r < N; ++r) {
       const double f = A[r][c] / A[c][c];
-      for (int k = c; k < 6; ++k) A[r][k] -= f * A[c][k];
+      for (int k = c; k < N; ++k) A[r][k] -= f * A[c][k];
       b[r] -= f * b[c];
     }
   }
-  for (int r = 5; r >= 0; --r) {
+  for (int r = N - 1; r >= 0; --r) {
     double t = b[r];
-    for (int k = r + 1; k < 6; ++k) t -= A[r][k] * b[k];
+    for (int k = r + 1; k < N; ++k) t -= A[r][k] * b[k];
     b[r] = t / A[r][r];
   }
   return true;
 }
-}  // namespace
 
-int b200icp_lum_seed_cache(b200icp_ctx* ctx, size_t limit_bytes) {
-  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
-  CU_TRY(cudaSetDevice(ctx->device));
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->lum_seeds.clear();
-  ctx->lum_seed_bytes = 0;
-  ctx->lum_seed_limit = limit_bytes;
-  return B200ICP_OK;
-}
-
-int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
-                     double max_dist_match2, double C[36], double CD[6], uint64_t* npairs) {
+// shared body of b200icp_lum_link (Euler, 6 parameters) and b200icp_lum_link_quat (7 parameters)
+template <bool QUAT>
+int lum_link_impl(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second, double max_dist_match2,
+                  double* C, double* CD, uint64_t* npairs) {
+  constexpr int N = QUAT ? 7 : 6;
   if (!ctx || !first || !second || !C || !CD) return fail(B200ICP_EINVAL, "lum_link: NULL argument");
   if (!(max_dist_match2 >= 0.0)) return fail(B200ICP_EINVAL, "lum_link: max_dist_match2 must be >= 0");
   CU_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  for (int i = 0; i < 36; ++i) C[i] = 0.0;
-  for (int i = 0; i < 6; ++i) CD[i] = 0.0;
+  for (int i = 0; i < N * N; ++i) C[i] = 0.0;
+  for (int i = 0; i < N; ++i) CD[i] = 0.0;
   if (npairs) *npairs = 0;
   // per-link neighbour cache: the pairs of this link's previous evaluation seed the searches of this one (the graph
   // relaxation evaluates every link once per iteration and the poses move little in between)
@@ -1099,52 +1094,84 @@ int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_
   memcpy(hx, second->dalignxf, 16 * sizeof(double));
   memcpy(hx + 16, first->dalignxf, 16 * sizeof(double));
   m4_inverse(first->dalignxf, hx + 32);
-  for (int i = 0; i < 6; ++i) hx[48 + i] = 0.0;
-  CU_TRY(cudaMemcpyAsync(ctx->d_small.p, hx, 54 * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < 7; ++i) hx[48 + i] = 0.0;
+  CU_TRY(cudaMemcpyAsync(ctx->d_small.p, hx, 55 * sizeof(double), cudaMemcpyHostToDevice, st));
   const uint32_t nd = (uint32_t)second->n;
   const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
   const int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)(ctx->sm_count * 2));
-  std::vector<double> hp((size_t)grid * 16);
-  lum_link_kernel<1><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
-                                              cache, ctx->partials.p, seeded);
+  std::vector<double> hp((size_t)grid * kLumSums);
+  lum_link_kernel<1, QUAT><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
+                                                    cache, ctx->partials.p, seeded);
   CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());
-  double s[16] = {0};
+  double s[kLumSums] = {0};
   for (int b = 0; b < grid; ++b)
-    for (int k = 0; k < 16; ++k) s[k] += hp[(size_t)b * 16 + k];
+    for (int k = 0; k < kLumSums; ++k) s[k] += hp[(size_t)b * kLumSums + k];
   const double m = s[0];
   if (npairs) *npairs = (uint64_t)(m + 0.5);
   if (!(m > 2.0)) return B200ICP_OK;   // "This case should not occur": C = CD = 0 (lum6Deuler.cc:243-259)
   const double sx = s[1], sy = s[2], sz = s[3], xpy = s[4], xpz = s[5], ypz = s[6], xy = s[7], xz = s[8], yz = s[9];
-  double MM[6][6] = {{0}}, MZ[6] = {s[10], s[11], s[12], s[13], s[14], s[15]};
+  double MM[N][N] = {{0}}, MZ[N];
   MM[0][0] = MM[1][1] = MM[2][2] = m;
-  MM[3][3] = ypz; MM[4][4] = xpy; MM[5][5] = xpz;
-  MM[0][4] = MM[4][0] = -sy; MM[0][5] = MM[5][0] = sz;
-  MM[1][3] = MM[3][1] = -sz; MM[1][4] = MM[4][1] = sx;
-  MM[2][3] = MM[3][2] = sy;  MM[2][5] = MM[5][2] = -sx;
-  MM[3][4] = MM[4][3] = -xz; MM[3][5] = MM[5][3] = -xy; MM[4][5] = MM[5][4] = -yz;
-  double A[6][6], D[6];
+  if (!QUAT) {                         // lum6Deuler.cc:177-191
+    for (int i = 0; i < 6; ++i) MZ[i] = s[10 + i];
+    MM[3][3] = ypz; MM[4][4] = xpy; MM[5][5] = xpz;
+    MM[0][4] = MM[4][0] = -sy; MM[0][5] = MM[5][0] = sz;
+    MM[1][3] = MM[3][1] = -sz; MM[1][4] = MM[4][1] = sx;
+    MM[2][3] = MM[3][2] = sy;  MM[2][5] = MM[5][2] = -sx;
+    MM[3][4] = MM[4][3] = -xz; MM[3][5] = MM[5][3] = -xy; MM[4][5] = MM[5][4] = -yz;
+  } else {                             // lum6Dquat.cc:166-188 (1-based there)
+    MZ[0] = s[10]; MZ[1] = s[11]; MZ[2] = s[12]; MZ[3] = s[16]; MZ[4] = s[13]; MZ[5] = s[14]; MZ[6] = s[15];
+    MM[3][3] = s[17]; MM[4][4] = ypz; MM[5][5] = xpz; MM[6][6] = xpy;
+    MM[0][3] = MM[3][0] = sx; MM[0][5] = MM[5][0] = -sz; MM[0][6] = MM[6][0] = sy;
+    MM[1][3] = MM[3][1] = sy; MM[1][4] = MM[4][1] = sz;  MM[1][6] = MM[6][1] = -sx;
+    MM[2][3] = MM[3][2] = sz; MM[2][4] = MM[4][2] = -sy; MM[2][5] = MM[5][2] = sx;
+    MM[4][5] = MM[5][4] = -xy; MM[4][6] = MM[6][4] = -xz; MM[5][6] = MM[6][5] = -yz;
+  }
+  double A[N][N], D[N];
   memcpy(A, MM, sizeof A);
   memcpy(D, MZ, sizeof D);
-  if (!gauss6(A, D)) return B200ICP_OK;
-  memcpy(hx + 48, D, sizeof D);
-  CU_TRY(cudaMemcpyAsync(ctx->d_small.p + 48, hx + 48, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-  lum_link_kernel<2><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
-                                              cache, ctx->partials.p, 0);
+  if (!gauss_solve<N>(A, D)) return B200ICP_OK;
+  for (int i = 0; i < 7; ++i) hx[48 + i] = i < N ? D[i] : 0.0;
+  CU_TRY(cudaMemcpyAsync(ctx->d_small.p + 48, hx + 48, 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+  lum_link_kernel<2, QUAT><<<grid, kBlock, 0, st>>>(first->g, second->g.p64, nd, ctx->d_small.p, max_dist_match2,
+                                                    cache, ctx->partials.p, 0);
   CU_TRY(cudaMemcpyAsync(hp.data(), ctx->partials.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   CU_TRY(cudaGetLastError());
   double ss = 0.0;
-  for (int b = 0; b < grid; ++b) ss += hp[(size_t)b * 16];
+  for (int b = 0; b < grid; ++b) ss += hp[(size_t)b * kLumSums];
   ss = ss / (2.0 * m - 3.0);
-  if (ss < 0.0000000000001) return B200ICP_OK;   // identical clouds (lum6Deuler.cc:219-231)
-  ss = 1.0 / ss;
-  for (int i = 0; i < 6; ++i) {
+  if (!QUAT && ss < 0.0000000000001) return B200ICP_OK;   // identical clouds (lum6Deuler.cc:219-231; the quaternion
+  ss = 1.0 / ss;                                           // form has no such guard, lum6Dquat.cc:208-209)
+  for (int i = 0; i < N; ++i) {
     CD[i] = MZ[i] * ss;
-    for (int k = 0; k < 6; ++k) C[6 * i + k] = MM[i][k] * ss;
+    for (int k = 0; k < N; ++k) C[N * i + k] = MM[i][k] * ss;
   }
   return B200ICP_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int b200icp_lum_seed_cache(b200icp_ctx* ctx, size_t limit_bytes) {
+  if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->lum_seeds.clear();
+  ctx->lum_seed_bytes = 0;
+  ctx->lum_seed_limit = limit_bytes;
+  return B200ICP_OK;
+}
+
+int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
+                     double max_dist_match2, double C[36], double CD[6], uint64_t* npairs) {
+  return lum_link_impl<false>(ctx, first, second, max_dist_match2, C, CD, npairs);
+}
+
+int b200icp_lum_link_quat(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
+                          double max_dist_match2, double C[49], double CD[7], uint64_t* npairs) {
+  return lum_link_impl<true>(ctx, first, second, max_dist_match2, C, CD, npairs);
 }
 
 // ------------------------------------------------------------------------------------ octree reduction

@@ -592,26 +592,28 @@ nn_batch_kernel(GridDev model, const double* __restrict__ q_xyz, const double* _
   block_reduce_store_regs<8>(acc, partials + (size_t)blockIdx.x * 8);
 }
 
-// ---- LUM link sums: lum6DEuler::covarianceEuler (reference src/slam6d/lum6Deuler.cc:94-260) ---------------
-// PASS 1: pairs of (model grid, data scan) -> neighbour cache + the 16 sums that make MM (6x6) and MZ (6).
+// ---- LUM link sums: lum6DEuler::covarianceEuler (reference src/slam6d/lum6Deuler.cc:94-260) and, with QUAT,
+// lum6DQuat::covarianceQuat (src/slam6d/lum6Dquat.cc:83-240, the 7-parameter form ELCH-SLERP uses) ---------------
+// PASS 1: pairs of (model grid, data scan) -> neighbour cache + the sums that make MM and MZ (16 Euler / 18 quat).
 // PASS 2: the pairs are re-formed from the cache (nothing moved) and the residual sum ss is taken with the
 //         pose-difference estimate D the host solved from pass 1 -- the reference's two walks over `uk`.
-// xfs: [0..15] data dalignxf, [16..31] model dalignxf, [32..47] its inverse, [48..53] D.
-// partials: [grid][16].  Sums are taken in absolute coordinates like the reference (the linearisation of
+// xfs: [0..15] data dalignxf, [16..31] model dalignxf, [32..47] its inverse, [48..54] D.
+// partials: [grid][kLumSums].  Sums are taken in absolute coordinates like the reference (the linearisation of
 // the LUM error is about the origin, so these moments are not shift-invariant).
-template <int PASS>
+constexpr int kLumSums = 18;
+template <int PASS, bool QUAT>
 __global__ void __launch_bounds__(kBlock, 2)
 lum_link_kernel(GridDev model, const double4* __restrict__ dq, uint32_t nd, const double* __restrict__ xfs,
                 double maxdist2, int* __restrict__ nn_cache, double* __restrict__ partials, int seeded) {
   __shared__ SearchSmemSmall sm;
-  __shared__ double X[16], S[16], Sinv[16], D[6];
+  __shared__ double X[16], S[16], Sinv[16], D[7];
   const int tid = threadIdx.x;
   if (tid < 16) { X[tid] = xfs[tid]; S[tid] = xfs[16 + tid]; Sinv[tid] = xfs[32 + tid]; }
-  if (tid < 6) D[tid] = xfs[48 + tid];
+  if (tid < 7) D[tid] = xfs[48 + tid];
   __syncthreads();
-  double acc[16];
+  double acc[kLumSums];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  for (int k = 0; k < kLumSums; ++k) acc[k] = 0.0;
   unsigned stage2 = 0;
   const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -650,16 +652,27 @@ lum_link_kernel(GridDev model, const double4* __restrict__ dq, uint32_t nd, cons
         acc[4] += x * x + y * y; acc[5] += x * x + z * z; acc[6] += y * y + z * z;
         acc[7] += x * y; acc[8] += x * z; acc[9] += y * z;
         acc[10] += dx; acc[11] += dy; acc[12] += dz;
-        acc[13] += -z * dy + y * dz; acc[14] += -y * dx + x * dy; acc[15] += z * dx - x * dz;
-      } else {
+        if (!QUAT) {
+          acc[13] += -z * dy + y * dz; acc[14] += -y * dx + x * dy; acc[15] += z * dx - x * dz;
+        } else {   // MZ(5..7), MZ(4) and the trace sum xpypz of lum6Dquat.cc:146-164
+          acc[13] += z * dy - y * dz; acc[14] += x * dz - z * dx; acc[15] += y * dx - x * dy;
+          acc[16] += x * dx + y * dy + z * dz;
+          acc[17] += x * x + y * y + z * z;
+        }
+      } else if (!QUAT) {
         const double rx = dx - (D[0] - y * D[4] + z * D[5]);
         const double ry = dy - (D[1] - z * D[3] + x * D[4]);
         const double rz = dz - (D[2] + y * D[3] - x * D[5]);
         acc[0] += rx * rx + ry * ry + rz * rz;
+      } else {     // lum6Dquat.cc:203-205
+        const double rx = dx - (D[0] + x * D[3] - z * D[5] + y * D[6]);
+        const double ry = dy - (D[1] + y * D[3] + z * D[4] - x * D[6]);
+        const double rz = dz - (D[2] + z * D[3] - y * D[4] + x * D[5]);
+        acc[0] += rx * rx + ry * ry + rz * rz;
       }
     }
   }
-  block_reduce_store_regs<16>(acc, partials + (size_t)blockIdx.x * 16);
+  block_reduce_store_regs<kLumSums>(acc, partials + (size_t)blockIdx.x * kLumSums);
 }
 
 // current "xyz reduced" = X * original (Scan::transformReduced), written back in original row order

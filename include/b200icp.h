@@ -222,6 +222,12 @@ int b200icp_last_profile(b200icp_ctx* ctx, int cap, double* nn_ms, double* solve
  * stays on the host (it is O(scans)). */
 int b200icp_lum_link(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
                      double max_dist_match2, double C[36], double CD[6], uint64_t* npairs);
+/* Replaces: lum6DQuat::covarianceQuat (src/slam6d/lum6Dquat.cc:83-240; caller: elch6Dslerp.cc:63) -- the same link
+ * in the 7-parameter (translation + quaternion) linearisation: 17 running sums, D = MM^-1 MZ (7x7), residual pass,
+ * C = MM / s^2 (row-major 7x7), CD = MZ / s^2.  C = CD = 0 with fewer than 3 pairs.  Same kernel, same neighbour
+ * cache as b200icp_lum_link. */
+int b200icp_lum_link_quat(b200icp_ctx* ctx, const b200icp_scan* first, const b200icp_scan* second,
+                          double max_dist_match2, double C[49], double CD[7], uint64_t* npairs);
 /* The context remembers, per (first, second) link, the neighbour found for every point of `second` and uses it to
  * seed the link's next evaluation (the graph relaxation evaluates each link once per iteration while the poses
  * barely move; a seed only bounds the search radius, the pairs do not depend on it).  This call drops all remembered

@@ -191,8 +191,8 @@ double reff_lum_euler(void** hs, int n, const int* links, int nlinks, int nr_it,
   CoutSilencer quiet;
   lum6DEuler lum(mini, max_dist_match_lum, 25.0, 50, true, false, 1, true, -1, 1e-7, nns_method, epsilon_lum);
   Graph g;
-  g.setNrScans(n);
   for (int i = 0; i < nlinks; ++i) g.addLink(links[2 * i], links[2 * i + 1]);
+  g.setNrScans(n);   // (addLink counts nodes as it meets them; the scan count is what the caller says, as Graph(netfile))
   const double r = lum.doGraphSlam6D(g, as_scans(hs, n), nr_it);
   delete mini;
   return r;

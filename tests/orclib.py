@@ -2,6 +2,8 @@
 
   port()  -> oracle/_build/liboracle_icp.so   our CPU restatement (built on demand with g++)
   ref()   -> oracle/_ref/libref3dtk.so        the compiled, unmodified reference (None if absent)
+  full()  -> oracle/_ref/libref3dtk_full.so   the reference's own Scan / icp6D / lum6DEuler / BOctTree classes
+                                              (oracle/full_harness.cc; None if absent)
 Both are checkers only; nothing in the product imports this module.
 """
 import ctypes as C
@@ -15,6 +17,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 PORT_SO = os.path.join(ORACLE_DIR, "_build", "liboracle_icp.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk.so")
 REF_OMP_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk_omp.so")
+REF_FULL_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk_full.so")
 
 vp, cl, ci, cd = C.c_void_p, C.c_long, C.c_int, C.c_double
 _port = None
@@ -89,6 +92,93 @@ def ref(omp=False):
             L.ref_lum_link.restype = cl; L.ref_lum_link.argtypes = [vp, vp, vp, cl, cd, vp, vp]
             _ref[path] = L
     return _ref[path]
+
+
+_full = []
+
+
+def full():
+    """oracle/_ref/libref3dtk_full.so (the reference's own classes, see oracle/full_harness.cc) or None."""
+    if not _full:
+        if not os.path.exists(REF_FULL_SO):
+            _full.append(None)
+        else:
+            L = C.CDLL(REF_FULL_SO)
+            L.reff_scan_create.restype = vp
+            L.reff_scan_create.argtypes = [vp, cl, vp, vp, cd, ci, ci, ci]
+            L.reff_scan_free_all.restype = None; L.reff_scan_free_all.argtypes = [vp, ci]
+            L.reff_scan_get.restype = cl; L.reff_scan_get.argtypes = [vp, C.c_char_p, vp, cl]
+            L.reff_scan_pose.restype = None; L.reff_scan_pose.argtypes = [vp] * 5
+            L.reff_scan_frames.restype = cl; L.reff_scan_frames.argtypes = [vp, vp, vp, cl]
+            L.reff_scan_transform.restype = None; L.reff_scan_transform.argtypes = [vp, vp, ci, ci]
+            L.reff_match.restype = ci; L.reff_match.argtypes = [vp, vp, ci, ci, cd, ci, cd, ci, ci]
+            L.reff_do_icp.restype = ci; L.reff_do_icp.argtypes = [vp, ci, ci, ci, cd, ci, cd, ci, ci, ci, ci, ci]
+            L.reff_covariance.restype = ci; L.reff_covariance.argtypes = [vp, vp, ci, ci, ci, cd, vp, vp]
+            L.reff_graph_from_poses.restype = ci; L.reff_graph_from_poses.argtypes = [ci, cd, ci, vp, ci]
+            L.reff_lum_euler.restype = cd; L.reff_lum_euler.argtypes = [vp, ci, vp, ci, ci, cd, cd, ci]
+            _full.append(L)
+    return _full[0]
+
+
+class FullRefScans:
+    """A set of the reference's own in-memory BasicScans (scan-local points + pose), freed together.
+    `with FullRefScans(locals_xyz, rpos, rpostheta, voxel=-1) as fr: ...`"""
+
+    def __init__(self, locals_xyz, rpos, rpostheta, voxel=-1.0, nrpts=0, nns=0, bucket=20):
+        self.L = full()
+        self.h = (vp * len(locals_xyz))()
+        for i, (x, p, t) in enumerate(zip(locals_xyz, rpos, rpostheta)):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            p = np.ascontiguousarray(p, dtype=np.float64); t = np.ascontiguousarray(t, dtype=np.float64)
+            self.h[i] = self.L.reff_scan_create(P(x), len(x), P(p), P(t), float(voxel), nrpts, nns, bucket)
+        self.n = len(locals_xyz)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.L.reff_scan_free_all(self.h, self.n)
+
+    def get(self, i, field="xyz reduced"):
+        n = self.L.reff_scan_get(self.h[i], field.encode(), None, 0)
+        out = np.zeros((n, 3))
+        self.L.reff_scan_get(self.h[i], field.encode(), P(out), n)
+        return out
+
+    def pose(self, i):
+        T, D, p, t = np.zeros(16), np.zeros(16), np.zeros(3), np.zeros(3)
+        self.L.reff_scan_pose(self.h[i], P(T), P(D), P(p), P(t))
+        return {"transmat": T, "dalignxf": D, "rpos": p, "rpostheta": t}
+
+    def frames(self, i):
+        n = self.L.reff_scan_frames(self.h[i], None, None, 0)
+        mats, types = np.zeros((n, 16)), np.zeros(n, dtype=np.int32)
+        self.L.reff_scan_frames(self.h[i], P(mats), types.ctypes.data, n)
+        return mats, types
+
+    def match(self, prev, cur, algo=1, mode=0, max_dist=25.0, max_iter=50, eps=1e-5, rnd=1):
+        return self.L.reff_match(self.h[prev], self.h[cur], algo, mode, max_dist, max_iter, eps, rnd, 0)
+
+    def do_icp(self, algo=1, mode=0, max_dist=25.0, max_iter=50, eps=1e-5, meta=False, extrapolate_pose=True,
+               max_num_metascans=-1):
+        return self.L.reff_do_icp(self.h, self.n, algo, mode, max_dist, max_iter, eps, 1, int(meta),
+                                  int(extrapolate_pose), max_num_metascans, 0)
+
+    def covariance(self, first, second, maxdist2, quat=False):
+        dim = 7 if quat else 6
+        Cm, CD = np.zeros((dim, dim)), np.zeros(dim)
+        self.L.reff_covariance(self.h[first], self.h[second], int(quat), 0, 1, maxdist2, P(Cm), P(CD))
+        return Cm, CD
+
+    def graph_from_poses(self, cldist2, loopsize):
+        cap = self.n * self.n + 1
+        links = np.zeros((cap, 2), dtype=np.int32)
+        m = self.L.reff_graph_from_poses(self.n, cldist2, loopsize, links.ctypes.data, cap)
+        return links[:m].copy()
+
+    def lum_euler(self, links, nr_it, max_dist_lum=25.0, eps_lum=0.5):
+        links = np.ascontiguousarray(links, dtype=np.int32)
+        return self.L.reff_lum_euler(self.h, self.n, links.ctypes.data, len(links), nr_it, max_dist_lum, eps_lum, 0)
 
 
 def P(a):
@@ -247,8 +337,8 @@ def octree_centres(pts, voxel):
     """Oracle for the `-r voxel` reduction (numpy restatement of include/slam6d/Boctree.h:224-270, :612-656,
     :928-949, :1164-1195, :1353-1355): root cube = bbox centre, half-size = max half-extent + 1.0; child index bit
     k set iff p[k] > centre[k]; a child is a leaf when ITS half-size <= voxel; output = leaf-cube centres, depth
-    first, children 0..7.  PARITY UNPINNED against compiled reference code: Boctree.h needs Boost.Interprocess and
-    cannot be built here; the restatement follows the source line by line."""
+    first, children 0..7.  Pinned: bit-identical to Scan::calcReducedPoints + BOctTree of the compiled reference
+    (oracle/_ref/libref3dtk_full.so) -- tests/test_full_reference.py, golden tests/golden/full_vectors.npz."""
     import sys
     pts = np.asarray(pts, dtype=np.float64)
     mins, maxs = pts.min(0), pts.max(0)
