@@ -18,6 +18,7 @@ PORT_SO = os.path.join(ORACLE_DIR, "_build", "liboracle_icp.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk.so")
 REF_OMP_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk_omp.so")
 REF_FULL_SO = os.path.join(ORACLE_DIR, "_ref", "libref3dtk_full.so")
+ADAPTER_FULL_SO = os.path.join(ORACLE_DIR, "_ref", "libadapter3dtk_full.so")
 
 vp, cl, ci, cd = C.c_void_p, C.c_long, C.c_int, C.c_double
 _port = None
@@ -95,15 +96,12 @@ def ref(omp=False):
 
 
 _full = []
+_adapter_full = []
 
 
-def full():
-    """oracle/_ref/libref3dtk_full.so (the reference's own classes, see oracle/full_harness.cc) or None."""
-    if not _full:
-        if not os.path.exists(REF_FULL_SO):
-            _full.append(None)
-        else:
-            L = C.CDLL(REF_FULL_SO)
+def _full_sigs(L):
+    if True:
+        if True:
             L.reff_scan_create.restype = vp
             L.reff_scan_create.argtypes = [vp, cl, vp, vp, cd, ci, ci, ci]
             L.reff_scan_free_all.restype = None; L.reff_scan_free_all.argtypes = [vp, ci]
@@ -116,22 +114,67 @@ def full():
             L.reff_covariance.restype = ci; L.reff_covariance.argtypes = [vp, vp, ci, ci, ci, cd, vp, vp]
             L.reff_graph_from_poses.restype = ci; L.reff_graph_from_poses.argtypes = [ci, cd, ci, vp, ci]
             L.reff_lum_euler.restype = cd; L.reff_lum_euler.argtypes = [vp, ci, vp, ci, ci, cd, cd, ci]
-            _full.append(L)
+    return L
+
+
+def full():
+    """oracle/_ref/libref3dtk_full.so (the reference's own classes, see oracle/full_harness.cc) or None."""
+    if not _full:
+        _full.append(_full_sigs(C.CDLL(REF_FULL_SO)) if os.path.exists(REF_FULL_SO) else None)
     return _full[0]
+
+
+def adapter_full():
+    """oracle/_ref/libadapter3dtk_full.so: the same classes + the reference-side adapters (icp6D_gpu, GpuSearchTree)
+    + the product library (oracle/adapter_full_harness.cc); None if absent.  Needs a GPU to do anything."""
+    if not _adapter_full:
+        if not os.path.exists(ADAPTER_FULL_SO):
+            _adapter_full.append(None)
+        else:
+            L = _full_sigs(C.CDLL(ADAPTER_FULL_SO))
+            L.reffa_last_error.restype = C.c_char_p
+            L.reffa_scan_create_gputree.restype = vp
+            L.reffa_scan_create_gputree.argtypes = [vp, cl, vp, vp, cd, ci, cd]
+            L.reffa_match_gpu.restype = ci; L.reffa_match_gpu.argtypes = [vp, vp, ci, ci, cd, ci, cd, ci, ci, vp]
+            L.reffa_do_icp_gpu.restype = ci; L.reffa_do_icp_gpu.argtypes = [vp, ci, ci, ci, cd, ci, cd, ci, ci, ci, ci]
+            _adapter_full.append(L)
+    return _adapter_full[0]
 
 
 class FullRefScans:
     """A set of the reference's own in-memory BasicScans (scan-local points + pose), freed together.
     `with FullRefScans(locals_xyz, rpos, rpostheta, voxel=-1) as fr: ...`"""
 
-    def __init__(self, locals_xyz, rpos, rpostheta, voxel=-1.0, nrpts=0, nns=0, bucket=20):
-        self.L = full()
+    def __init__(self, locals_xyz, rpos, rpostheta, voxel=-1.0, nrpts=0, nns=0, bucket=20, lib=None, gpu_tree=False,
+                 max_dist_hint=25.0):
+        """lib: full() (default) or adapter_full(); gpu_tree (adapter_full only): the scans' search tree is a
+        GpuSearchTree instead of the k-d tree."""
+        self.L = lib if lib is not None else full()
         self.h = (vp * len(locals_xyz))()
         for i, (x, p, t) in enumerate(zip(locals_xyz, rpos, rpostheta)):
             x = np.ascontiguousarray(x, dtype=np.float64)
             p = np.ascontiguousarray(p, dtype=np.float64); t = np.ascontiguousarray(t, dtype=np.float64)
-            self.h[i] = self.L.reff_scan_create(P(x), len(x), P(p), P(t), float(voxel), nrpts, nns, bucket)
+            if gpu_tree:
+                self.h[i] = self.L.reffa_scan_create_gputree(P(x), len(x), P(p), P(t), float(voxel), nrpts, max_dist_hint)
+            else:
+                self.h[i] = self.L.reff_scan_create(P(x), len(x), P(p), P(t), float(voxel), nrpts, nns, bucket)
         self.n = len(locals_xyz)
+
+    def match_gpu(self, prev, cur, algo=1, mode=0, max_dist=25.0, max_iter=50, eps=1e-5, rnd=1, anim=-1):
+        """icp6D_gpu::match through an icp6D* -> (return value, iterations_run, npairs_last, kernel launches)"""
+        out = (C.c_long * 3)()
+        it = self.L.reffa_match_gpu(self.h[prev], self.h[cur], algo, mode, max_dist, max_iter, eps, rnd, anim, out)
+        if it == -1000:
+            raise RuntimeError(self.L.reffa_last_error().decode())
+        return it, out[0], out[1], out[2]
+
+    def do_icp_gpu(self, algo=1, mode=0, max_dist=25.0, max_iter=50, eps=1e-5, meta=False, extrapolate_pose=True,
+                   max_num_metascans=-1):
+        rc = self.L.reffa_do_icp_gpu(self.h, self.n, algo, mode, max_dist, max_iter, eps, 1, int(meta),
+                                     int(extrapolate_pose), max_num_metascans)
+        if rc == -1000:
+            raise RuntimeError(self.L.reffa_last_error().decode())
+        return rc
 
     def __enter__(self):
         return self
