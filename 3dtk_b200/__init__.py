@@ -45,6 +45,9 @@ class MatchResult(C.Structure):
                 ("stage2_queries_last", C.c_uint32)]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_size_t, C.c_void_p)   # b200icp_allreduce_fn
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -104,6 +107,8 @@ def _load():
         "b200icp_lum_fill_gb": (i32, [vp, dp, i32, dp, i32, f64, dp, dp, dp]),
         "b200icp_lum_solve_update": (i32, [dp, i32, dp, dp, C.POINTER(f64), vp]),
         "b200icp_lum_graph_slam": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, C.POINTER(f64), C.POINTER(i32), vp]),
+        "b200icp_lum_graph_slam_sharded": (i32, [vp, dp, i32, dp, i32, f64, i32, f64, i32, i32, ALLREDUCE_FN, vp,
+                                                 C.POINTER(f64), C.POINTER(i32), vp]),
         "b200icp_matrix4_to_euler": (None, [dp, dp, dp]),
         "b200icp_scan_calc_normals": (i32, [vp, vp, i32, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
@@ -563,6 +568,30 @@ class lum6DEuler:
         _check(lib.b200icp_lum_graph_slam(self.ctx._h, _scan_array(scans), len(scans), _ptr(links), links.shape[0],
                                           self.max_dist_match2_lum, int(nr_it), self.epsilon_lum, C.byref(ret),
                                           C.byref(it), frames._h if frames is not None else None))
+        return ret.value, it.value
+
+    def doGraphSlam6D_sharded(self, graph, scans, nr_it, rank, world, allreduce, frames=None):
+        """b200icp_lum_graph_slam_sharded: links round-robin over `world` ranks, `allreduce(buf)` sums the packed
+        [G|B] numpy view in place over the ranks (called once per LUM iteration) -> (ret, iterations run)"""
+        ret, it = C.c_double(0.0), C.c_int(0)
+        links = np.ascontiguousarray(graph.links, dtype=np.int32)
+        err = []
+
+        def _cb(ptr, count, _user):
+            try:
+                allreduce(np.ctypeslib.as_array(ptr, shape=(count,)))
+                return 0
+            except Exception as ex:      # never let an exception cross the C frame
+                err.append(ex)
+                return 1
+        cb = ALLREDUCE_FN(_cb)
+        rc = lib.b200icp_lum_graph_slam_sharded(self.ctx._h, _scan_array(scans), len(scans), _ptr(links), links.shape[0],
+                                                self.max_dist_match2_lum, int(nr_it), self.epsilon_lum, int(rank),
+                                                int(world), cb, None, C.byref(ret), C.byref(it),
+                                                frames._h if frames is not None else None)
+        if err:
+            raise err[0]
+        _check(rc)
         return ret.value, it.value
 
 

@@ -255,4 +255,43 @@ int b200icp_lum_graph_slam(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_s
   return B200ICP_OK;
 }
 
+int b200icp_lum_graph_slam_sharded(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
+                                   int n_links, double max_dist_match2, int nr_it, double epsilon_lum, int rank,
+                                   int world, b200icp_allreduce_fn allreduce, void* user, double* ret_out,
+                                   int* iterations_out, b200icp_frames* frames) {
+  if (!ctx || !scans || !links) return b200icp_set_error_(B200ICP_EINVAL, "lum_graph_slam_sharded: NULL argument");
+  if (n_scans <= 0) return b200icp_set_error_(B200ICP_EINVAL, "Zero scans in graph");   // lum6Deuler.cc:316-318
+  if (world < 1 || rank < 0 || rank >= world)
+    return b200icp_set_error_(B200ICP_EINVAL, "lum_graph_slam_sharded: need 0 <= rank < world");
+  if (world > 1 && !allreduce)
+    return b200icp_set_error_(B200ICP_EINVAL, "lum_graph_slam_sharded: world > 1 needs an all-reduce callback");
+  // this rank's links: round-robin (consecutive links cost about the same; the reference hands them out with
+  // `schedule(dynamic)`, lum6Deuler.cc:271)
+  std::vector<int> mine;
+  for (int l = rank; l < n_links; l += world) { mine.push_back(links[2 * l]); mine.push_back(links[2 * l + 1]); }
+  double ret = DBL_MAX;
+  int it = 0;
+  if (n_scans >= 2) {
+    const int dim = 6 * (n_scans - 1);
+    std::vector<double> GB((size_t)dim * dim + dim);          // [G | B] packed: ONE all-reduce per LUM iteration
+    for (; it < nr_it && ret > epsilon_lum; ++it) {
+      std::fill(GB.begin(), GB.end(), 0.0);
+      int rc = b200icp_lum_fill_gb(ctx, scans, n_scans, mine.data(), (int)(mine.size() / 2), max_dist_match2,
+                                   GB.data(), GB.data() + (size_t)dim * dim, nullptr);
+      if (rc != B200ICP_OK) return rc;
+      if (world > 1 && allreduce(GB.data(), GB.size(), user) != 0)
+        return b200icp_set_error_(B200ICP_ESTATE, "lum_graph_slam_sharded: the all-reduce callback failed");
+      // every rank now holds the same system and runs the same O(scans) solve + pose update on its replica of the
+      // scans: the replicas stay bit-identical without a broadcast
+      double sum = 0.0;
+      rc = b200icp_lum_solve_update(scans, n_scans, GB.data(), GB.data() + (size_t)dim * dim, &sum, frames);
+      if (rc != B200ICP_OK) return rc;
+      ret = sum / (double)n_scans;
+    }
+  }
+  if (ret_out) *ret_out = ret;
+  if (iterations_out) *iterations_out = it;
+  return B200ICP_OK;
+}
+
 }  // extern "C"

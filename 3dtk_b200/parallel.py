@@ -85,18 +85,22 @@ def reduce_timing(elapsed_s, units, group=None, device=None):
 
 def graph_slam_sharded(lum, graph, scans, nr_it, rank, world_size, group=None, device=None, frames=None):
     """lum6DEuler::doGraphSlam6D with the links of FillGB3D sharded over ranks (SURVEY 8e-B, the north-star's
-    "NCCL allreduce only for the global lum6D covariance sum").  Every rank holds all scans on its own GPU; per LUM
-    iteration it fills G, B from ITS links (`b200icp_lum_fill_gb` -> lum_link_kernel), ONE all-reduce makes the
-    system global, and every rank runs the identical O(scans) solve + pose update (`b200icp_lum_solve_update`), so
-    the replicated scans stay in lock-step without a broadcast.  Returns (ret, iterations) like doGraphSlam6D."""
-    n = len(scans)
-    if n <= 0:
+    "NCCL allreduce only for the global lum6D covariance sum").  The loop itself is the C ABI's
+    `b200icp_lum_graph_slam_sharded` (what a C++ host calls with an MPI / NCCL callback); this wrapper only supplies
+    the all-reduce: ONE `torch.distributed.all_reduce` of the packed [G|B] fp64 buffer per LUM iteration ("nccl" on
+    the GPU box -- staged through `device` --, "gloo" in the CPU tests).  Returns (ret, iterations)."""
+    import torch
+    import torch.distributed as dist
+    if len(scans) <= 0:
         raise ValueError("Zero scans in graph")            # lum6Deuler.cc:316-318
-    mine = shard_units(graph.get_nr_links(), rank, world_size)
-    ret, it = float("inf"), 0
-    while it < nr_it and ret > lum.epsilon_lum and n >= 2:
-        G, B, _ = lum.fill_gb(graph, scans, link_subset=mine)
-        G, B = allreduce_gb(G, B, group=group, device=device)
-        ret = lum.solve_update(scans, G, B, frames=frames) / float(n)
-        it += 1
-    return ret, it
+
+    def allreduce(buf):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        t = torch.from_numpy(buf)
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        buf[:] = t.cpu().numpy()
+
+    return lum.doGraphSlam6D_sharded(graph, scans, nr_it, rank, world_size, allreduce, frames=frames)

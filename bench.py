@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--shard", default="pairs", choices=["pairs", "queries"],
                     help="pairs: one scan pair per GPU (weak scaling, default, north_star); queries: ONE pair, data\n"
                          "points split across GPUs, moments all-reduced inside the kernel over NVLink (strong scaling)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the multi-GPU objects of the line (strong: query-sharded pair; lum_link_sharded: configs[3])")
     ap.add_argument("--rows", action="store_true",
                     help="instead of the configs[1] line: measure the SURVEY 8f rows (octree reduction, normals, LUM link,\n"
                          "graph relaxation, metascan, uos reader), one JSON object per row (tests/rows_bench.py)")
@@ -259,6 +261,111 @@ def cpu_reference_run(model, data, max_iter, matches, serial_semantics=False):
             "iterations": total_it, "matches": matches, "last": last}
 
 
+def strong_section(icp, torch, dist, local_rank, rank, world, a, t1_ms):
+    """SURVEY 8e-A under the driver: ONE 1M pair, the data scan split across the ranks (the split of
+    Scan::getPtPairsParallel, scan.cc:1335-1342), pair moments all-reduced INSIDE the iteration kernel over NVLink
+    peer memory.  Returns the `strong` object of the JSON line (rank 0) or None."""
+    stream = torch.cuda.current_stream()
+    ctx = icp.Context(local_rank, stream=stream.cuda_stream)
+    model, data, _ = make_pair(icp, a.points, 0)
+    step_q = -(-len(data) // world)
+    mine = np.ascontiguousarray(data[rank * step_q:min((rank + 1) * step_q, len(data))])
+    handle = ctx.comm_create(rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    ctx.comm_connect_ipc(handles)
+    dist.barrier()
+    m_scan = icp.Scan(ctx, model, max_dist_hint=25.0)
+    d_scan = icp.Scan(ctx, mine, max_dist_hint=25.0)
+    eng = icp.icp6D(ctx, algo=icp.ALGO_QUAT, max_dist_match=25.0, max_num_iterations=a.max_iter, epsilon_icp=1e-5,
+                    exact=bool(a.exact), sharded=True)
+    ident = np.eye(4).reshape(16).copy()
+    steps = max(3, min(a.steps, 10))
+    tot, iters, last = 0.0, 0, None
+    for k in range(3 + steps):
+        d_scan.set_pose(ident, ident)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = eng.match(m_scan, d_scan)
+        e1.record(stream); e1.synchronize()
+        if k >= 3:
+            tot += e0.elapsed_time(e1); iters += last["iterations_run"]
+    v = torch.tensor([tot], dtype=torch.float64, device="cuda")
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    T = d_scan.get_pose()[0]
+    chk = torch.tensor(T, dtype=torch.float64, device="cuda")
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ms = float(v[0]) / steps
+    it = iters / steps
+    out = {"workload": "ONE %d x %d pair, data points split over %d GPUs (scan.cc:1335-1342), pair moments "
+                       "all-reduced in the iteration kernel through NVLink peer mailboxes (no NCCL on the path)"
+                       % (a.points, a.points, world),
+           "ms_per_match": ms, "iterations_per_match": it, "n1_ms_per_match": t1_ms,
+           "speedup_vs_n1": t1_ms / ms, "efficiency": t1_ms / (world * ms),
+           "value": a.points * it / (ms * 1e-3), "unit": UNIT, "steps": steps,
+           "pose_bit_identical_across_ranks": bool(torch.equal(lo, hi)),
+           "fixed_us_per_iteration": 1e3 * (ms - t1_ms / world) / max(it, 1),
+           "limiter": "per-iteration fixed cost (kernel launch + last-block reduction + serial 6-DoF solve + mailbox "
+                      "flag round trip over NVLink) does not shrink with N: fixed_us_per_iteration = (t_N - t_1 / N) "
+                      "/ iterations"}
+    m_scan.destroy(); d_scan.destroy()
+    dist.barrier()
+    ctx.close()
+    return out if rank == 0 else None
+
+
+def lum_section(icp, torch, dist, local_rank, rank, world):
+    """SURVEY 8e-B exchange step under the driver: BASELINE configs[3]'s global relaxation (65 scans x 300k points,
+    replicated per GPU), graph links sharded round-robin, ONE all-reduce of the packed [G|B] per LUM iteration
+    (b200icp_lum_graph_slam_sharded; NCCL through torch.distributed).  Seeding of the link searches from the previous
+    LUM iteration is on (default).  Returns the `lum_link_sharded` object (rank 0) or None."""
+    par = importlib.import_module("3dtk_b200.parallel")
+    n_scans, n_pts = int(os.environ.get("B200_BENCH_LUM_SCANS", 65)), int(os.environ.get("B200_BENCH_LUM_PTS", 300_000))
+    ctx = icp.Context(local_rank)
+    rng = np.random.default_rng(4)
+    dev, T = [], []
+    for i in range(n_scans):      # registered sequence with a small residual error per scan (what ICP leaves behind)
+        Pm = icp.euler_to_matrix4(rng.normal(0, 0.5, 3), np.deg2rad(rng.normal(0, 0.05, 3))) if i else np.eye(4).reshape(16)
+        sc = icp.Scan(ctx, icp.transform_points(Pm, icp.synth_scene(7, 1400 + i, n_pts, 0.5)), max_dist_hint=25.0)
+        sc.set_pose(Pm, None)
+        dev.append(sc); T.append(Pm)
+    rpos = np.array([icp.matrix4_to_euler(t)[0] for t in T])
+    graph = icp.Graph.from_poses(rpos, 750.0 ** 2, 20)
+    lum = icp.lum6DEuler(ctx, max_dist_match_lum=25.0, epsilon_lum=-1.0)
+    device = torch.device("cuda", local_rank)
+    par.graph_slam_sharded(lum, graph, dev, 1, rank, world, device=device)      # warm-up iteration (unseeded)
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    iters = 3
+    t0 = time.perf_counter()
+    ret, it = par.graph_slam_sharded(lum, graph, dev, iters, rank, world, device=device)
+    ctx.synchronize()
+    el = time.perf_counter() - t0
+    tmax, links = par.reduce_timing(el, len(par.shard_units(graph.get_nr_links(), rank, world)) * iters, device=device)
+    poses = torch.tensor(np.array([d.get_pose()[0] for d in dev]).reshape(-1), dtype=torch.float64, device=device)
+    identical = True
+    if dist is not None:
+        lo, hi = poses.clone(), poses.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo, hi))
+    for d in dev:
+        d.destroy()
+    ctx.close()
+    if rank != 0:
+        return None
+    dim = 6 * (n_scans - 1)
+    return {"workload": "BASELINE configs[3] relaxation: %d scans x %d points replicated per GPU, %d links (Graph(n, 750^2, "
+                        "20)), -D 25, links round-robin over %d rank(s)" % (n_scans, n_pts, graph.get_nr_links(), world),
+            "s_per_lum_iteration": tmax / iters, "link_evaluations_per_s": links / tmax, "lum_iterations": iters,
+            "seeded": True, "allreduce_bytes_per_iteration": 8 * (dim * dim + dim) if world > 1 else 0,
+            "collective": "one torch.distributed all_reduce (NCCL) of the packed fp64 [G|B] per LUM iteration" if world > 1 else "none (1 rank)",
+            "poses_bit_identical_across_ranks": identical, "ret": ret,
+            "timing": "wall clock around %d LUM iterations after one warm-up iteration, max over ranks" % iters}
+
+
 def main():
     a = parse()
     if a.rows:   # single GPU, rank 0 only; the CPU arms of these rows execute the oracle, hence under tests/
@@ -434,6 +541,7 @@ def main():
     clocks = sampler.stop()   # sampled across both timed regions (resident steps and e2e steps)
 
     # ---- reduce over ranks: max time, summed work
+    ms_total_local = ms_total
     vals = torch.tensor([ms_total, float(iters_total), e2e_t, float(e2e_it), float(launches)],
                         dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -443,6 +551,20 @@ def main():
         iters_sum, e2e_it_sum, launches = float(sm[1]), float(sm[3]), int(sm[4])
     else:
         iters_sum, e2e_it_sum = float(iters_total), float(e2e_it)
+    strong = lum_obj = None
+    if not a.no_extra and not shard_q:
+        if world > 1:
+            # t_1 of the same pair: rank 0's own (weak) pair IS pair 0
+            t1 = torch.tensor([ms_total_local / a.steps if rank == 0 else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            try:
+                strong = strong_section(icp, torch, dist, local_rank, rank, world, a, float(t1[0]))
+            except Exception as ex:
+                strong = {"error": repr(ex)}
+        try:
+            lum_obj = lum_section(icp, torch, dist, local_rank, rank, world)
+        except Exception as ex:
+            lum_obj = {"error": repr(ex)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -493,6 +615,10 @@ def main():
                     "d2h_bytes_per_step": 2 * 640 * max(1, (a.max_iter + 3) // 4) + 16 * a.max_iter,
                     "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches, "roofline": roofline}
+    if strong is not None:
+        line["strong"] = strong
+    if lum_obj is not None:
+        line["lum_link_sharded"] = lum_obj
     line["timing_note"] = ("value / e2e count every iteration of the match incl. iteration 0 (the reference's own "
                            "timer starts at iteration 1, icp6D.cc:127); grid build is outside `value`, inside `e2e`")
     if world == 1 and not a.no_parity:

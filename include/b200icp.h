@@ -262,6 +262,18 @@ int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const doub
 int b200icp_lum_graph_slam(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
                            int n_links, double max_dist_match2, int nr_it, double epsilon_lum,
                            double* ret_out, int* iterations_out, b200icp_frames* frames);
+/* Link-sharded relaxation (the north-star's "allreduce only for the global lum6D covariance sum"), for
+ * a host that runs one process per GPU: rank r of `world` holds ALL scans on its device, evaluates links r, r + world,
+ * ... (lum6Deuler.cc:271-298 hands the links of FillGB3D to OpenMP threads the same way), and the packed fp64 buffer
+ * [G | B] ((6(n-1))^2 + 6(n-1) doubles, host memory) is summed over the ranks by the caller's `allreduce` -- one call
+ * per LUM iteration: wrap MPI_Allreduce, ncclAllReduce on a staging buffer, or torch.distributed (3dtk_b200/parallel.py
+ * does the latter).  Every rank then runs the identical solve + pose update, so the replicated scans stay bit-identical
+ * without a broadcast.  The callback returns 0 on success; world == 1 never calls it. */
+typedef int (*b200icp_allreduce_fn)(double* sum_inout, size_t count, void* user);
+int b200icp_lum_graph_slam_sharded(b200icp_ctx* ctx, b200icp_scan* const* scans, int n_scans, const int* links,
+                                   int n_links, double max_dist_match2, int nr_it, double epsilon_lum, int rank,
+                                   int world, b200icp_allreduce_fn allreduce, void* user, double* ret_out,
+                                   int* iterations_out, b200icp_frames* frames);
 void b200icp_matrix4_to_euler(const double m[16], double rPosTheta[3], double rPos[3]);
 
 /* ---- scan files and frames (the wire formats either side of the path; host only) -----------
