@@ -45,6 +45,7 @@ METRIC = "icp_correspondences_per_sec"
 UNIT = "correspondences/s"
 POSE_POS = (12.0, -7.0, 5.0)
 POSE_THETA_DEG = (0.5, -1.0, 0.8)
+FP32_PEAK_FLOPS = 148 * 128 * 2 * 1.965e9   # B200 non-tensor fp32 (B200_PROFILING.md: 148 SMs, 1965 MHz)
 
 
 def parse():
@@ -200,8 +201,9 @@ def peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the correspondence kernel from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when absent."""
+    """DRAM bytes and candidate evaluations per launch of the correspondence kernel from the committed
+    `ncu --set full` captures of THIS tree (profiles/ncu_traffic.json, written by tools/gpu_roofline.sh +
+    tools/ncu_traffic.py); (None, None) when absent."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
@@ -595,6 +597,14 @@ def main():
                 "traffic_source": (ncu_traffic()[1] or {}).get("source"),
                 "algorithmic_bytes_per_launch": b_alg, "kernel_ms": nn_ms, "iteration_ms": iter_ms,
                 "peak_source": peak_src,
+                "candidate_evals_per_s": (ncu_traffic()[1] or {}).get("candidate_evaluations_per_s_mean"),
+                "candidate_evals_fp32_frac": ((ncu_traffic()[1] or {}).get("candidate_evaluations_per_s_mean") or 0.0) * 8.0 / FP32_PEAK_FLOPS
+                                             if ncu_traffic()[1] else None,
+                "candidate_evals_note": "SURVEY 8d second figure: fp32 squared-distance evaluations per second (ncu source "
+                                        "counters of iterations 1/15/40, profiles/ncu_traffic.json) x 8 flop-equivalents "
+                                        "against the B200's non-tensor fp32 peak (148 SMs x 128 lanes x 2 x 1.965 GHz = "
+                                        "74.4 TFLOP/s): the distance arithmetic is ~15 % of the kernel's instructions, the "
+                                        "rest walks cells and ranges (profiles/r02_ncu_lines_iter1.txt)",
                 "note": "B_alg = 16*N_d + 16*N_m + 8*N_occupied_cells + 512 per ICP iteration (SURVEY 8d); the "
                         "kernel is bound by L1/L2 latency and instruction issue of the candidate scan, not by HBM "
                         "(model + tables fit the 126 MB L2), see DESIGN.md section 4"}
