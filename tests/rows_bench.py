@@ -110,6 +110,37 @@ else:
 row("f3 MetaScan search structure over %d x %d points" % (ns, npts), "metaScan.cc:27-69 / kdMeta.cc:34-72", ns * npts, "points", g,
     (32 + 24) * ns * npts + 48 * ns * npts, c, cu, kind, "export of every member through dalignxf + grid build, all on device")
 
+# ---- b drop-in `-t gpu`: the reference's OWN serial icp6D::match loop (compiled unmodified: scan.cc, icp6D.cc,
+# searchTree.cc, icp6Dquat.cc) over a GpuSearchTree as the scan's tree, next to the same loop over its k-d tree, and
+# icp6D_gpu::match (the fused path behind the same virtual) -- 1M x 1M pair, oracle/_ref/libadapter3dtk_full.so
+AL = orclib.adapter_full()
+if AL is not None:
+    n = 1_000_000
+    model = icp.synth_scene(7, 42, n, 0.5)
+    data = icp.transform_points(icp.m4inv(icp.euler_to_matrix4(np.array([12.0, -7.0, 5.0]), np.deg2rad([0.5, -1.0, 0.8])))[0],
+                                icp.synth_scene(7, 43, n, 0.5))
+    Zz = np.zeros(3)
+
+    def loop(gpu_tree, iters):
+        with orclib.FullRefScans([model, data], [Zz, Zz], [Zz, Zz], lib=AL, gpu_tree=gpu_tree) as fr:
+            fr.get(0, "xyz reduced"); fr.get(1, "xyz reduced")           # on-demand copies outside the time
+            AL.reff_match(fr.h[0], fr.h[1], 1, 0, 25.0, 1, 1e-5, 1, 0)   # builds the tree (first getPtPairs), 1 iteration
+            t = time.perf_counter()
+            it = AL.reff_match(fr.h[0], fr.h[1], 1, 0, 25.0, iters, 1e-5, 1, 0)
+            return (time.perf_counter() - t) / (it + 1)
+
+    s_gpu_tree = loop(True, 6)
+    s_kd = loop(False, 2)
+    with orclib.FullRefScans([model, data], [Zz, Zz], [Zz, Zz], lib=AL) as fr:
+        fr.get(0, "xyz reduced"); fr.get(1, "xyz reduced")
+        t = time.perf_counter(); it, ran, _, _ = fr.match_gpu(0, 1, algo=1, max_iter=50); s_fused = time.perf_counter() - t
+    row("b drop-in -t gpu: reference icp6D::match loop (serial, PtPair vector, Align walk) over GpuSearchTree",
+        "icp6D.cc:104-285 / searchTree.h:38-113", n, "queries per iteration", s_gpu_tree, 24 * n + 4 * n, s_kd, n,
+        "the same unmodified loop over the reference KDtree (1 core)",
+        "per ICP iteration; the GPU tree answers one b200icp_nn_batch per getPtPairs call, PtPairs (208 B each) are rebuilt "
+        "on the host; icp6D_gpu::match (fused path, whole %d-iteration match incl. upload, grid build and the host replay "
+        "of every Scan::transform) takes %.3f s = %.1f ms per iteration" % (ran, s_fused, 1e3 * s_fused / max(ran, 1)))
+
 # ---- f4 uos reader: 1M lines
 pts = icp.synth_scene(7, 920, 1_000_000, 0.5)
 with tempfile.TemporaryDirectory() as td:
