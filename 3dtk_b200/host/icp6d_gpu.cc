@@ -137,20 +137,33 @@ int icp6D_gpu::match(Scan* PreviousScan, Scan* CurrentScan, PairingMode pairing_
     iter = last_.iterations;
     nr_pointPair = (int)last_.npairs_last;
 
-    // ---- replay on the host scan: one Scan::transform per iteration that produced a transform, with the frame rule of
-    // icp6D.cc:258-264 (a frame after iteration 0 and every anim'th one), then the end pose (:266-279)
+    // ---- replay on the host scan with the frame rule of icp6D.cc:258-264: the transform of an iteration that writes
+    // a frame (iteration 0 and every anim'th one) is applied by its own Scan::transform(.., ICP, 0); the transforms
+    // of the iterations in between write no frame (islum = -1 in the reference), so they are composed and applied by
+    // ONE Scan::transform(.., ICP, -1) -- same frames, same final transMat / dalignxf / points up to the rounding of
+    // the composition, and the host walks the scan's points 3 times per match instead of once per iteration
     const int ran = last_.iterations_run;
     std::vector<double> poses(16 * (size_t)(ran > 0 ? ran : 1));
     if (ran > 0 && b200icp_last_poses(ctx_, ran, poses.data()) < ran) raise("last_poses");
-    double prev[16], inv[16], alignxf[16];
+    double prev[16], inv[16], alignxf[16], pending[16], tmp[16];
+    bool has_pending = false;
+    M4identity(pending);
     memcpy(prev, T0, sizeof prev);
     for (int k = 0; k < ran; ++k) {
       M4inv(prev, inv);
       MMult(&poses[16 * (size_t)k], inv, alignxf);            // alignxf_k = T_k * T_{k-1}^-1
       const bool frame = (k == 0 && anim != -2) || (anim > 0 && k % anim == 0);
-      CurrentScan->transform(alignxf, Scan::ICP, frame ? 0 : -1);
+      if (frame) {
+        if (has_pending) { CurrentScan->transform(pending, Scan::ICP, -1); M4identity(pending); has_pending = false; }
+        CurrentScan->transform(alignxf, Scan::ICP, 0);
+      } else {
+        MMult(alignxf, pending, tmp);
+        memcpy(pending, tmp, sizeof pending);
+        has_pending = true;
+      }
       memcpy(prev, &poses[16 * (size_t)k], sizeof prev);
     }
+    if (has_pending) CurrentScan->transform(pending, Scan::ICP, -1);
     // the loop ends through its convergence test / iteration cap with an end-pose frame, or leaves early
     // ("do we have enough point pairs?", :233-241) without one
     if (ran > 0 && ran == iter + 1) CurrentScan->transform(id, Scan::ICP, anim == -2 ? -1 : 0);

@@ -12,6 +12,7 @@
 //   loop    b200icp_match: every iteration of the loop on the device in the reference's arithmetic order
 //   result  replayed on the host through Scan::transform with the reference's own frame rule (icp6D.cc:258-279):
 //           CurrentScan's points, transMat, dalignxf and every scan's frames end up as the CPU loop leaves them
+//           (iterations that write no frame are composed into one Scan::transform call)
 //
 // Minimizers: the algorithm id of the icp6Dminimizer selects the on-device solve (1 QUAT, 2 SVD, 3 ORTHO, 4 DUAL,
 // 5 HELIX, 6 APX, 10 NAPX); anything else throws std::runtime_error -- there is no CPU fallback in this class.
