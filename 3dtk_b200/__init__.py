@@ -113,6 +113,8 @@ def _load():
         "b200icp_scan_calc_normals": (i32, [vp, vp, i32, dp]),
         "b200icp_normals_knn": (i32, [vp, dp, sz, i32, dp, dp]),
         "b200icp_reduce_octree_center": (i32, [vp, dp, sz, f64, dp, C.POINTER(sz)]),
+        "b200icp_reduce_octree": (i32, [vp, dp, dp, sz, f64, i32, C.c_uint, sz, dp, dp, C.POINTER(sz)]),
+        "b200icp_glibc_rand": (i32, [C.c_uint, sz, sz, dp]),
         "b200icp_synth_scene": (i32, [C.c_uint64, C.c_uint64, sz, f64, dp]),
         "b200icp_euler_to_matrix4": (None, [dp, dp, dp]),
         "b200icp_m4inv": (i32, [dp, dp]),
@@ -602,6 +604,24 @@ def reduce_octree_center(ctx, xyz, voxel_size):
     m = C.c_size_t(0)
     _check(lib.b200icp_reduce_octree_center(ctx._h, _ptr(xyz), xyz.shape[0], voxel_size, _ptr(out), C.byref(m)))
     return out[:m.value].copy()
+
+
+def reduce_octree(ctx, xyz, voxel_size, nrpts=0, normals=None, rand_seed=1, rand_skip=0):
+    """Scan::calcReducedPoints with -O nrpts (0 centre, -1 average, 1 one random point per voxel) -> xyz[, normals]"""
+    xyz = _f64(xyz, 3)
+    nrm = None if normals is None else _f64(normals, 3)
+    out = np.empty_like(xyz)
+    out_n = None if nrm is None else np.empty_like(xyz)
+    m = C.c_size_t(0)
+    _check(lib.b200icp_reduce_octree(ctx._h, _ptr(xyz), _ptr(nrm), len(xyz), float(voxel_size), int(nrpts),
+                                     int(rand_seed), int(rand_skip), _ptr(out), _ptr(out_n), C.byref(m)))
+    return out[:m.value].copy() if nrm is None else (out[:m.value].copy(), out_n[:m.value].copy())
+
+
+def glibc_rand(seed, count, skip=0):
+    out = np.empty(count, dtype=np.int32)
+    _check(lib.b200icp_glibc_rand(int(seed), int(skip), int(count), out.ctypes.data))
+    return out
 
 
 def normals_knn(ctx, xyz, k, rpos):

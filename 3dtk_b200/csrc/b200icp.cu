@@ -1232,6 +1232,112 @@ int b200icp_reduce_octree_center(b200icp_ctx* ctx, const double* xyz, size_t n, 
   return B200ICP_OK;
 }
 
+// glibc's rand() stream (random_r.c TYPE_3: r[i] = r[i-3] + r[i-31] over 32-bit words, seeded by the Lehmer
+// generator 16807 x mod 2^31-1, first 310 outputs discarded, result >> 1) -- what std::rand() returns on the Linux
+// builds of the reference; `skip` values are dropped first (calls the process made before the reduction).
+extern "C" int b200icp_glibc_rand(unsigned seed, size_t skip, size_t count, int* out) {
+  if (!out && count) return fail(B200ICP_EINVAL, "glibc_rand: out is NULL");
+  if (seed == 0) seed = 1;
+  std::vector<uint32_t> r(34 + 310 + skip + count);
+  r[0] = seed;
+  for (int i = 1; i < 31; ++i) {
+    long long w = (16807LL * (long long)(int32_t)r[i - 1]) % 2147483647LL;
+    if (w < 0) w += 2147483647LL;
+    r[i] = (uint32_t)w;
+  }
+  for (int i = 31; i < 34; ++i) r[i] = r[i - 31];
+  for (size_t i = 34; i < r.size(); ++i) r[i] = r[i - 31] + r[i - 3];
+  for (size_t k = 0; k < count; ++k) out[k] = (int)(r[344 + skip + k] >> 1);
+  return B200ICP_OK;
+}
+
+int b200icp_reduce_octree(b200icp_ctx* ctx, const double* xyz, const double* normals, size_t n, double voxel_size,
+                          int nrpts, unsigned rand_seed, size_t rand_skip, double* xyz_out, double* nrm_out,
+                          size_t* n_out) {
+  if (!ctx || !xyz || !xyz_out || !n_out) return fail(B200ICP_EINVAL, "reduce_octree: NULL argument");
+  if (nrpts == 0) {
+    if (normals || nrm_out)   // GetOctTreeCenter copies POINTDIM values out of a 3-value centre (Boctree.h:938-941)
+      return fail(B200ICP_EINVAL, "reduce_octree: centre extraction does not carry normals (the reference reads past its centre array there)");
+    return b200icp_reduce_octree_center(ctx, xyz, n, voxel_size, xyz_out, n_out);
+  }
+  if (nrpts != -1 && nrpts != 1)
+    return fail(B200ICP_EINVAL, "reduce_octree: nrpts must be 0 (centre), -1 (average) or 1 (one random point per voxel)");
+  if (!(voxel_size > 0.0)) return fail(B200ICP_EINVAL, "reduce_octree: voxel_size must be > 0");
+  if ((normals == nullptr) != (nrm_out == nullptr)) return fail(B200ICP_EINVAL, "reduce_octree: normals and nrm_out go together");
+  *n_out = 0;
+  if (n == 0) return B200ICP_OK;
+  if (n >= (1ull << 31)) return fail(B200ICP_EINVAL, "reduce_octree: more than 2^31-1 points");
+  CU_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> d_xyz, d_nrm, bb_part, bb_out, d_out, d_out_n;
+  CU_TRY(d_xyz.alloc_async(3 * n, st));
+  CU_TRY(cudaMemcpyAsync(d_xyz.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (normals) {
+    CU_TRY(d_nrm.alloc_async(3 * n, st));
+    CU_TRY(cudaMemcpyAsync(d_nrm.p, normals, 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  const int bb_blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 4);
+  CU_TRY(bb_part.alloc_async((size_t)bb_blocks * 6, st));
+  CU_TRY(bb_out.alloc_async(6, st));
+  bbox_partial_kernel<<<bb_blocks, 256, 0, st>>>(d_xyz.p, n, bb_part.p);
+  bbox_final_kernel<<<1, 32, 0, st>>>(bb_part.p, bb_blocks, bb_out.p);
+  double bb[6];
+  CU_TRY(cudaMemcpyAsync(bb, bb_out.p, sizeof bb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  for (int k = 0; k < 6; ++k)
+    if (!std::isfinite(bb[k])) return fail(B200ICP_EINVAL, "reduce_octree: non-finite coordinate");
+  OctRoot root;
+  for (int k = 0; k < 3; ++k) root.c[k] = 0.5 * (bb[k] + bb[3 + k]);             // Boctree.h:249-251
+  root.size = std::max(std::max(0.5 * (bb[3] - bb[0]), 0.5 * (bb[4] - bb[1])), 0.5 * (bb[5] - bb[2]));
+  root.size += 1.0;                                                              // Boctree.h:255
+  root.levels = 1;
+  for (double hs = root.size / 2.0; hs > voxel_size; hs /= 2.0) ++root.levels;
+  if (root.levels > 21) return fail(B200ICP_EINVAL, "reduce_octree: voxel too small for a 63-bit octree key");
+  DevBuf<unsigned long long> k_in, k_sorted;
+  DevBuf<uint32_t> r_in, r_sorted, heads;
+  DevBuf<unsigned char> flags, tmp;
+  DevBuf<int> d_count, d_rnd;
+  CU_TRY(k_in.alloc_async(n, st)); CU_TRY(k_sorted.alloc_async(n, st));
+  CU_TRY(r_in.alloc_async(n, st)); CU_TRY(r_sorted.alloc_async(n, st));
+  CU_TRY(heads.alloc_async(n, st)); CU_TRY(flags.alloc_async(n, st)); CU_TRY(d_count.alloc_async(1, st));
+  oct_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyz.p, n, root, k_in.p);
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r_in.p, n);
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, k_in.p, k_sorted.p, r_in.p, r_sorted.p, (int)n, 0, 3 * root.levels, st);
+  cub::CountingInputIterator<uint32_t> counting(0);
+  cub::DeviceSelect::Flagged(nullptr, b2, counting, flags.p, heads.p, d_count.p, (int)n, st);
+  CU_TRY(tmp.alloc_async(std::max(b1, b2) + 256, st));
+  // (radix sort is stable: the rows of one voxel stay in input order, the order the octree keeps them in its leaf)
+  cub::DeviceRadixSort::SortPairs(tmp.p, b1, k_in.p, k_sorted.p, r_in.p, r_sorted.p, (int)n, 0, 3 * root.levels, st);
+  oct_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(k_sorted.p, n, flags.p);
+  cub::DeviceSelect::Flagged(tmp.p, b2, counting, flags.p, heads.p, d_count.p, (int)n, st);
+  int m = 0;
+  CU_TRY(cudaMemcpyAsync(&m, d_count.p, sizeof m, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (m <= 0 || (size_t)m > n) return fail(B200ICP_ECUDA, "reduce_octree: bad voxel count");
+  CU_TRY(d_out.alloc_async(3 * (size_t)m, st));
+  if (normals) CU_TRY(d_out_n.alloc_async(3 * (size_t)m, st));
+  std::vector<int> h_rnd;
+  if (nrpts == 1) {
+    h_rnd.resize((size_t)m);
+    int rc = b200icp_glibc_rand(rand_seed, rand_skip, (size_t)m, h_rnd.data());
+    if (rc != B200ICP_OK) return rc;
+    CU_TRY(d_rnd.alloc_async((size_t)m, st));
+    CU_TRY(cudaMemcpyAsync(d_rnd.p, h_rnd.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+    oct_extract_kernel<1><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_xyz.p, d_nrm.p, r_sorted.p, heads.p, (size_t)m, n,
+                                                                      d_rnd.p, d_out.p, d_out_n.p);
+  } else {
+    oct_extract_kernel<-1><<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_xyz.p, d_nrm.p, r_sorted.p, heads.p, (size_t)m, n,
+                                                                       nullptr, d_out.p, d_out_n.p);
+  }
+  CU_TRY(cudaMemcpyAsync(xyz_out, d_out.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (normals) CU_TRY(cudaMemcpyAsync(nrm_out, d_out_n.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  *n_out = (size_t)m;
+  return B200ICP_OK;
+}
+
 // ------------------------------------------------------------------------------------ communicator
 int b200icp_comm_create(b200icp_ctx* ctx, int rank, int world, void* ipc_handle_out) {
   if (!ctx) return fail(B200ICP_EINVAL, "ctx is NULL");

@@ -1,4 +1,5 @@
-// reduce.cuh -- octree voxel-CENTRE reduction (the step right before the hot path).
+// reduce.cuh -- octree voxel reduction (the step right before the hot path): centre, average
+// and one-random-point-per-voxel extraction.
 //
 // Replaces Scan::calcReducedPoints + BOctTree construction + GetOctTreeCenter for `-r <voxel>` with the default
 // `-O 0` (reference src/slam6d/scan.cc:560-601; include/slam6d/Boctree.h:224-270 root cube, :612-656 child
@@ -8,9 +9,16 @@
 // depth-first output order.  Keys are computed with the reference's own centre arithmetic
 // (centre +- size/2.0, size halved per level) so points on a splitting plane fall on the same side, then
 // radix-sorted and made unique; the leaf-cube centre is re-derived from the key by the same walk.
+// Average / random extraction (GetOctTreeAvg Boctree.h:951-983, GetOctTreeRandom :985-1019, called from
+// scan.cc:585-601 for `-O -1` / `-O 1`): a STABLE sort of (key, row) keeps the points of a voxel in input order --
+// the order the octree stores them in its leaf -- so one thread per voxel walks its points exactly like the
+// reference's loop: sequential fp64 sums divided by the count (all attributes, i.e. xyz and, with a normal-carrying
+// PointType, the normals: scan.cc:544-557,652-676), or point number (int)(length * rand() / (RAND_MAX + 1.0)) with
+// the k-th voxel in depth-first order consuming the k-th value of the C library's rand() stream (globals.icc:607-610).
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include "common.cuh"
 
 namespace b200 {
@@ -55,6 +63,49 @@ __global__ void oct_centre_kernel(const unsigned long long* __restrict__ keys, s
     s = hs;
   }
   out[3 * i] = cx; out[3 * i + 1] = cy; out[3 * i + 2] = cz;
+}
+
+__global__ void iota_kernel(uint32_t* __restrict__ v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+
+// flags[i] = 1 where a new voxel starts in the sorted key array
+__global__ void oct_heads_kernel(const unsigned long long* __restrict__ keys, size_t n, unsigned char* __restrict__ flags) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// one thread per voxel: heads[v] .. heads[v+1] (or n) are its points in input order (rows[] = original row)
+// MODE -1: average (GetOctTreeAvg), MODE 1: one random point (GetOctTreeRandom(c)), rnd[v] = v-th rand() value
+template <int MODE>
+__global__ void oct_extract_kernel(const double* __restrict__ xyz, const double* __restrict__ nrm,
+                                   const uint32_t* __restrict__ rows, const uint32_t* __restrict__ heads, size_t m,
+                                   size_t n, const int* __restrict__ rnd, double* __restrict__ out_xyz,
+                                   double* __restrict__ out_nrm) {
+  const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= m) return;
+  const size_t a = heads[v], b = v + 1 < m ? heads[v + 1] : n;
+  const unsigned length = (unsigned)(b - a);
+  if (MODE == 1) {
+    // inline int rand(int rnd) { return (int)((double)rnd * (double)std::rand() / (RAND_MAX + 1.0)); }
+    const int pick = (int)((double)(int)length * (double)rnd[v] / (2147483647.0 + 1.0));
+    const size_t r = rows[a + (size_t)pick];
+    for (int k = 0; k < 3; ++k) out_xyz[3 * v + k] = xyz[3 * r + k];
+    if (nrm && out_nrm)
+      for (int k = 0; k < 3; ++k) out_nrm[3 * v + k] = nrm[3 * r + k];
+    return;
+  }
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (size_t j = a; j < b; ++j) {
+    const size_t r = rows[j];
+    s[0] += xyz[3 * r]; s[1] += xyz[3 * r + 1]; s[2] += xyz[3 * r + 2];
+    if (nrm) { s[3] += nrm[3 * r]; s[4] += nrm[3 * r + 1]; s[5] += nrm[3 * r + 2]; }
+  }
+  for (int k = 0; k < 3; ++k) out_xyz[3 * v + k] = s[k] / length;     // avgp[j] /= length (unsigned -> double)
+  if (nrm && out_nrm)
+    for (int k = 0; k < 3; ++k) out_nrm[3 * v + k] = s[3 + k] / length;
 }
 
 }  // namespace b200

@@ -325,6 +325,19 @@ int b200icp_scan_calc_normals(b200icp_ctx* ctx, b200icp_scan* scan, int k, const
  * xyz_out must hold n rows; *n_out receives the number written.  Host pointers. */
 int b200icp_reduce_octree_center(b200icp_ctx* ctx, const double* xyz, size_t n, double voxel_size,
                                  double* xyz_out, size_t* n_out);
+/* The other extraction modes of Scan::calcReducedPoints (scan.cc:585-601), with the PointType path that carries
+ * normals through the reduction (scan.cc:544-557,652-676): nrpts = 0 centre (as above; no normals -- the reference's
+ * GetOctTreeCenter copies POINTDIM values out of a 3-value centre, Boctree.h:938-941), -1 GetOctTreeAvg
+ * (Boctree.h:951-983: per voxel the sequential fp64 mean of every attribute, points in input order), 1
+ * GetOctTreeRandom (Boctree.h:985-1019: per voxel point number (int)(length * rand() / (RAND_MAX + 1.0)), the k-th
+ * voxel in depth-first order consuming the k-th value of std::rand()).  rand_seed / rand_skip: the C library stream
+ * to replay (glibc; seed 1 and skip 0 = a process that has not called rand() yet).  normals / nrm_out: both or
+ * neither.  Output order = the octree's depth-first leaf order. */
+int b200icp_reduce_octree(b200icp_ctx* ctx, const double* xyz, const double* normals, size_t n, double voxel_size,
+                          int nrpts, unsigned rand_seed, size_t rand_skip, double* xyz_out, double* nrm_out,
+                          size_t* n_out);
+/* glibc's rand() stream restated (random_r.c, TYPE_3): out[k] = the (skip + k)-th value rand() returns after srand(seed) */
+int b200icp_glibc_rand(unsigned seed, size_t skip, size_t count, int* out);
 
 /* ---- synthetic inputs (host only, no GPU needed) -------------------------
  * scene(geom_seed, sample_seed, n): indoor box room 2000x300x1000 cm + 4 interior walls + 20 boxes whose

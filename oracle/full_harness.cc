@@ -83,6 +83,26 @@ void* reff_scan_create(const double* xyz, long n, const double rPos[3], const do
   return h;
 }
 
+// same, with per-point normals ("normal" field) and a normal-carrying reduction PointType (scan.cc:440-444,544-557)
+void* reff_scan_create_normals(const double* xyz, const double* nrm, long n, const double rPos[3],
+                               const double rPosTheta[3], double voxel, int nrpts) {
+  Held* h = new Held();
+  h->xyz.assign(xyz, xyz + 3 * n);
+  std::vector<double*> pts(n);
+  for (long i = 0; i < n; ++i) pts[i] = &h->xyz[3 * i];
+  double p[3] = {rPos[0], rPos[1], rPos[2]}, t[3] = {rPosTheta[0], rPosTheta[1], rPosTheta[2]};
+  CoutSilencer quiet;
+  h->scan = new BasicScan(p, t, pts);
+  DataNormal dn(h->scan->create("normal", sizeof(double) * 3 * (size_t)n));
+  for (long i = 0; i < n; ++i) { dn[i][0] = nrm[3 * i]; dn[i][1] = nrm[3 * i + 1]; dn[i][2] = nrm[3 * i + 2]; }
+  h->scan->setReductionParameter(voxel, nrpts, PointType(PointType::USE_NORMAL));
+  h->scan->setSearchTreeParameter(simpleKD, 20);
+  Scan::allScans.push_back(h->scan);
+  return h;
+}
+
+void reff_srand(unsigned seed) { srand(seed); }
+
 void reff_scan_free_all(void** hs, int n) {
   for (int i = 0; i < n; ++i) {
     Held* h = (Held*)hs[i];

@@ -25,6 +25,20 @@ for v in full_case.OCT_VOXELS:
     with orclib.FullRefScans([cloud], [Z], [Z], voxel=v) as fr:
         out["oct_centres_v%g" % v] = fr.get(0, "xyz reduced")
     print("octree voxel", v, "->", len(out["oct_centres_v%g" % v]))
+# average / random extraction, normals carried through the reduction (PointType::USE_NORMAL)
+cloud_s = icp.synth_scene(7, 12, 8000, 0.5)          # a smaller cloud keeps the fixture small
+rngn = np.random.default_rng(3)
+cloud_n = rngn.normal(size=cloud_s.shape)
+cloud_n /= np.linalg.norm(cloud_n, axis=1)[:, None]
+for nrpts, tag in ((-1, "avg"), (1, "rnd")):
+    orclib.full().reff_srand(1)                      # the stream a fresh process sees
+    with orclib.FullRefScans([cloud_s], [Z], [Z], voxel=10.0, nrpts=nrpts, normals=[cloud_n]) as fr:
+        out["oct_%s_xyz" % tag] = fr.get(0, "xyz reduced")
+        out["oct_%s_nrm" % tag] = fr.get(0, "normal reduced")
+
+    print("octree -O", nrpts, "->", len(out["oct_%s_xyz" % tag]))
+with orclib.FullRefScans([cloud_s], [Z], [Z], voxel=10.0) as fr:
+    out["oct_small_centres"] = fr.get(0, "xyz reduced")
 dat = os.path.join("/root/reference", "dat", "scan001.3d")
 if os.path.exists(dat):
     pts = np.loadtxt(dat, skiprows=0)[:, :3] if open(dat).readline().count(" ") >= 2 else np.loadtxt(dat, skiprows=1)[:, :3]

@@ -104,6 +104,9 @@ def _full_sigs(L):
         if True:
             L.reff_scan_create.restype = vp
             L.reff_scan_create.argtypes = [vp, cl, vp, vp, cd, ci, ci, ci]
+            L.reff_scan_create_normals.restype = vp
+            L.reff_scan_create_normals.argtypes = [vp, vp, cl, vp, vp, cd, ci]
+            L.reff_srand.restype = None; L.reff_srand.argtypes = [C.c_uint]
             L.reff_scan_free_all.restype = None; L.reff_scan_free_all.argtypes = [vp, ci]
             L.reff_scan_get.restype = cl; L.reff_scan_get.argtypes = [vp, C.c_char_p, vp, cl]
             L.reff_scan_pose.restype = None; L.reff_scan_pose.argtypes = [vp] * 5
@@ -146,7 +149,7 @@ class FullRefScans:
     `with FullRefScans(locals_xyz, rpos, rpostheta, voxel=-1) as fr: ...`"""
 
     def __init__(self, locals_xyz, rpos, rpostheta, voxel=-1.0, nrpts=0, nns=0, bucket=20, lib=None, gpu_tree=False,
-                 max_dist_hint=25.0):
+                 max_dist_hint=25.0, normals=None):
         """lib: full() (default) or adapter_full(); gpu_tree (adapter_full only): the scans' search tree is a
         GpuSearchTree instead of the k-d tree."""
         self.L = lib if lib is not None else full()
@@ -154,7 +157,10 @@ class FullRefScans:
         for i, (x, p, t) in enumerate(zip(locals_xyz, rpos, rpostheta)):
             x = np.ascontiguousarray(x, dtype=np.float64)
             p = np.ascontiguousarray(p, dtype=np.float64); t = np.ascontiguousarray(t, dtype=np.float64)
-            if gpu_tree:
+            if normals is not None:
+                nm = np.ascontiguousarray(normals[i], dtype=np.float64)
+                self.h[i] = self.L.reff_scan_create_normals(P(x), P(nm), len(x), P(p), P(t), float(voxel), nrpts)
+            elif gpu_tree:
                 self.h[i] = self.L.reffa_scan_create_gputree(P(x), len(x), P(p), P(t), float(voxel), nrpts, max_dist_hint)
             else:
                 self.h[i] = self.L.reff_scan_create(P(x), len(x), P(p), P(t), float(voxel), nrpts, nns, bucket)

@@ -46,6 +46,34 @@ def test_config3_point_to_plane_napx_full_size(icp, ctx):
     assert np.array_equal(idx >= 0, wi >= 0) and np.array_equal(d2[wi >= 0], wd[wi >= 0])
 
 
+def test_config3_full_size_parity_vs_compiled_reference(icp, ctx):
+    """configs[2] with the reference's OWN arithmetic (icp6D_NAPX as shipped, napx_weighted = 0) at full size against
+    the compiled reference (oracle/_ref: kd.cc / searchTree.cc / icp6Dnapx.cc; serial-arm arithmetic, k-d tree searches
+    spread over the host cores -- oracle/ref_harness.cc): same iterations, same pair count in every iteration, pose
+    within the north-star gate (in practice ~1e-10)."""
+    import os
+    if orclib.ref(omp=True) is None:
+        pytest.skip("oracle/_ref/libref3dtk_omp.so not built (needs /root/reference)")
+    n = 1_000_000
+    model, data, _ = make_pair(icp, n, n)
+    m = icp.Scan(ctx, model, max_dist_hint=25.0)
+    d = icp.Scan(ctx, data, max_dist_hint=25.0)
+    d.calc_normals(10, np.array([0.0, 150.0, 0.0]))                 # on the resident scan (no host round trip)
+    _, nrm = d.download(with_normals=True)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except Exception:
+        threads = os.cpu_count() or 1
+    want = orclib.ref_match(model, data, data_nrm=nrm, algo=10, mode=2, max_dist=25.0, max_iter=50, eps=1e-5,
+                            threads=-min(threads, 256), omp=True)
+    got = icp.icp6D(ctx, algo=icp.ALGO_NAPX, max_dist_match=25.0, max_num_iterations=50, epsilon_icp=1e-5,
+                    napx_weighted=False).match(m, d, icp.CLOSEST_PLANE_SIMPLE)
+    T, _ = d.get_pose()
+    assert got["iterations"] == want["iterations"]
+    assert np.array_equal(got["npairs"], want["npairs"])
+    assert orclib.rel_frobenius(T, want["transmat"]) < 1e-7 < 1e-4
+
+
 # ---- configs[3]: scan sequence, sequential ICP + metascan, then LUM over a pose-distance graph (SURVEY 3.4/3.5)
 def test_config4_sequence_metascan_then_lum_vs_oracle(icp, ctx):
     n_scans, n_pts = 6, 12000

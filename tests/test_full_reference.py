@@ -62,6 +62,35 @@ def test_gpu_octree_equals_reference(icp, ctx, gold):
         assert np.array_equal(got, gold["oct_centres_v%g" % v])
 
 
+@pytest.mark.gpu
+def test_gpu_octree_average_and_random_with_normals_equal_reference(icp, ctx, gold):
+    """-O -1 (GetOctTreeAvg) and -O 1 (GetOctTreeRandom, glibc rand() stream of a fresh process) with the PointType
+    that carries normals through the reduction: bit-identical to Scan::calcReducedPoints of the compiled reference."""
+    cloud = icp.synth_scene(7, 12, 8000, 0.5)
+    rngn = np.random.default_rng(3)
+    nrm = rngn.normal(size=cloud.shape)
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    for nrpts, tag in ((-1, "avg"), (1, "rnd")):
+        xyz, n = icp.reduce_octree(ctx, cloud, 10.0, nrpts=nrpts, normals=nrm, rand_seed=1, rand_skip=0)
+        assert np.array_equal(xyz, gold["oct_%s_xyz" % tag]), tag
+        assert np.array_equal(n, gold["oct_%s_nrm" % tag]), tag
+    # without normals, and the centre mode through the general entry point
+    assert np.array_equal(icp.reduce_octree(ctx, cloud, 10.0, nrpts=-1), gold["oct_avg_xyz"])
+    assert np.array_equal(icp.reduce_octree(ctx, cloud, 10.0, nrpts=0), gold["oct_small_centres"])
+    with pytest.raises(icp.B200ICPError):
+        icp.reduce_octree(ctx, cloud, 10.0, nrpts=3)
+
+
+def test_glibc_rand_restatement(icp):
+    import ctypes as C
+    libc = C.CDLL("libc.so.6")
+    for seed in (1, 2024):
+        libc.srand(seed)
+        want = np.array([libc.rand() for _ in range(1000)], dtype=np.int32)
+        assert np.array_equal(icp.glibc_rand(seed, 1000), want)
+        assert np.array_equal(icp.glibc_rand(seed, 10, skip=990), want[990:])
+
+
 # ------------------------------------------------------------------ f3: doICP
 def _doicp_key(eP, meta, mx):
     return "doicp_eP%d_meta%d_max%d" % (eP, meta, mx)
