@@ -5,16 +5,20 @@
 // `-O 0` (reference src/slam6d/scan.cc:560-601; include/slam6d/Boctree.h:224-270 root cube, :612-656 child
 // centres, :1353-1355 child index, :1164-1195 leaf rule, :928-949 centre extraction).
 // The octree is never built: a point's path from the root is a sequence of 3-bit child indices
-// (bit k set iff p[k] > centre[k], strict), i.e. a Morton-like key whose numeric order IS the reference's
+// (bit k set iff !(p[k] < centre[k]): Scan::calcReducedPoints builds the tree through the T** constructor, whose
+// partition keeps `p < split` on the lower side, Boctree.h:268,1784-1815 -- a point ON a splitting plane goes to the
+// upper child; pinned by a known-answer test against the compiled reference), i.e. a Morton-like key whose numeric order IS the reference's
 // depth-first output order.  Keys are computed with the reference's own centre arithmetic
 // (centre +- size/2.0, size halved per level) so points on a splitting plane fall on the same side, then
 // radix-sorted and made unique; the leaf-cube centre is re-derived from the key by the same walk.
 // Average / random extraction (GetOctTreeAvg Boctree.h:951-983, GetOctTreeRandom :985-1019, called from
-// scan.cc:585-601 for `-O -1` / `-O 1`): a STABLE sort of (key, row) keeps the points of a voxel in input order --
-// the order the octree stores them in its leaf -- so one thread per voxel walks its points exactly like the
-// reference's loop: sequential fp64 sums divided by the count (all attributes, i.e. xyz and, with a normal-carrying
-// PointType, the normals: scan.cc:544-557,652-676), or point number (int)(length * rand() / (RAND_MAX + 1.0)) with
-// the k-th voxel in depth-first order consuming the k-th value of the C library's rand() stream (globals.icc:607-610).
+// scan.cc:585-601 for `-O -1` / `-O 1`): a stable sort of (key, row) groups the points of a voxel (in input order);
+// one thread per voxel walks them like the reference's loop: sequential fp64 sums divided by the count (all
+// attributes, i.e. xyz and, with a normal-carrying PointType, the normals: scan.cc:544-557,652-676), or point number
+// (int)(length * rand() / (RAND_MAX + 1.0)) with the k-th voxel in depth-first order consuming the k-th value of the
+// C library's rand() stream (globals.icc:607-610).  The reference keeps a leaf's points in the order its unstable
+// (Hoare) partitions leave them, not in input order: averages agree to rounding (~1e-15), the random mode picks the
+// same NUMBER in every voxel but counts it through a differently ordered list -- another point of the same voxel.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -37,7 +41,7 @@ __global__ void oct_key_kernel(const double* __restrict__ xyz, size_t n, OctRoot
   double cx = root.c[0], cy = root.c[1], cz = root.c[2], s = root.size;
   unsigned long long key = 0;
   for (int l = 0; l < root.levels; ++l) {
-    const unsigned bx = px > cx, by = py > cy, bz = pz > cz;
+    const unsigned bx = !(px < cx), by = !(py < cy), bz = !(pz < cz);
     const double hs = s / 2.0;
     cx = bx ? cx + hs : cx - hs;
     cy = by ? cy + hs : cy - hs;

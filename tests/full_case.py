@@ -28,3 +28,7 @@ def cov_pair(icp):
     model = icp.synth_scene(7, 42, 20000, 0.5)
     data = icp.synth_scene(7, 43, 15000, 0.5)
     return model, data, np.array([3.0, -2.0, 1.5]), np.deg2rad(np.array([0.2, -0.3, 0.25]))
+
+
+# points ON splitting planes of the octree: bbox [0,4]^3 -> root centre (2,2,2), half-size 3
+OCT_PLANE_KAT = np.array([[0, 0, 0], [4, 4, 4], [2, 2, 2], [2, 1, 3], [1, 2, 3]], dtype=np.float64)

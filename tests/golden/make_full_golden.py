@@ -39,6 +39,8 @@ for nrpts, tag in ((-1, "avg"), (1, "rnd")):
     print("octree -O", nrpts, "->", len(out["oct_%s_xyz" % tag]))
 with orclib.FullRefScans([cloud_s], [Z], [Z], voxel=10.0) as fr:
     out["oct_small_centres"] = fr.get(0, "xyz reduced")
+with orclib.FullRefScans([full_case.OCT_PLANE_KAT], [Z], [Z], voxel=0.4) as fr:
+    out["oct_plane_kat"] = fr.get(0, "xyz reduced")
 dat = os.path.join("/root/reference", "dat", "scan001.3d")
 if os.path.exists(dat):
     pts = np.loadtxt(dat, skiprows=0)[:, :3] if open(dat).readline().count(" ") >= 2 else np.loadtxt(dat, skiprows=1)[:, :3]

@@ -384,8 +384,8 @@ def port_lum_graph_slam(scans_xyz, links, maxdist2, nr_it, eps, transmats, dalig
 
 def octree_centres(pts, voxel):
     """Oracle for the `-r voxel` reduction (numpy restatement of include/slam6d/Boctree.h:224-270, :612-656,
-    :928-949, :1164-1195, :1353-1355): root cube = bbox centre, half-size = max half-extent + 1.0; child index bit
-    k set iff p[k] > centre[k]; a child is a leaf when ITS half-size <= voxel; output = leaf-cube centres, depth
+    :928-949, :1164-1195, :268, :1784-1815): root cube = bbox centre, half-size = max half-extent + 1.0; child index bit
+    k set iff not p[k] < centre[k] (the T** constructor's partition: a point ON a splitting plane goes up); a child is a leaf when ITS half-size <= voxel; output = leaf-cube centres, depth
     first, children 0..7.  Pinned: bit-identical to Scan::calcReducedPoints + BOctTree of the compiled reference
     (oracle/_ref/libref3dtk_full.so) -- tests/test_full_reference.py, golden tests/golden/full_vectors.npz."""
     import sys
@@ -397,8 +397,8 @@ def octree_centres(pts, voxel):
 
     def rec(idx, c, s):            # node with centre c, half-size s, points idx
         p = pts[idx]
-        child = (p[:, 0] > c[0]).astype(np.int64) | ((p[:, 1] > c[1]).astype(np.int64) << 1) | \
-                ((p[:, 2] > c[2]).astype(np.int64) << 2)
+        child = (~(p[:, 0] < c[0])).astype(np.int64) | ((~(p[:, 1] < c[1])).astype(np.int64) << 1) | \
+                ((~(p[:, 2] < c[2])).astype(np.int64) << 2)
         for i in range(8):
             sel = idx[child == i]
             if len(sel) == 0:

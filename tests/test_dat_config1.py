@@ -62,7 +62,8 @@ def test_gpu_octree_reduction_matches_oracle(icp, ctx):
         got = icp.reduce_octree_center(ctx, raw, voxel)
         want = orclib.octree_centres(raw, voxel)
         assert got.shape == want.shape and np.array_equal(got, want)      # same centres, same depth-first order, bit-exact
-    # points exactly on splitting planes (strict '>' decides, Boctree.h:1353-1355) and a larger synthetic cloud
+    # points exactly on splitting planes (they go to the upper child: Boctree.h:268,1784-1815; known answer from the
+    # compiled reference in tests/test_full_reference.py) and a larger synthetic cloud
     grid = np.stack(np.meshgrid(*[np.arange(-8.0, 9.0, 2.0)] * 3, indexing="ij"), -1).reshape(-1, 3)
     assert np.array_equal(icp.reduce_octree_center(ctx, grid, 1.0), orclib.octree_centres(grid, 1.0))
     big = icp.synth_scene(7, 61, 200000, 0.5)
