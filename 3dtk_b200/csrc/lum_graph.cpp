@@ -58,7 +58,9 @@ bool cholesky_solve(int n, std::vector<double>& A, const double* b, double* x) {
       double sum = A[(size_t)i * n + j];
       for (int k = i - 1; k >= 0; --k) sum -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
       if (i == j) {
-        if (sum < 1.0e-7) return false;   // the pivot floor of the reference's choldc (globals.icc:829)
+        // not positive definite; the reference's default solver (cs_cholsol, graphSlam6D.cc:330) fails on the same
+        // condition -- no pivot floor, so weakly constrained but valid systems still solve
+        if (!(sum > 0.0)) return false;
         diag[i] = sqrt(sum);
       } else {
         A[(size_t)j * n + i] = sum / diag[i];
@@ -208,16 +210,13 @@ int b200icp_lum_solve_update(b200icp_scan* const* scans, int n_scans, const doub
     double nPos[3], nTh[3];
     for (int k = 0; k < 3; ++k) { nPos[k] = rPos[k] - result[k]; nTh[k] = rTh[k] - result[k + 3]; }
     // Scan::transformToEuler: transform(M4inv(transMat)) then transform(EulerToMatrix4(new pose))
-    double tinv[16], alignxf[16], t1[16], t2[16];
+    // (two Scan::transform calls, so that the scan's cumulative normal map follows as transform3normal would move the
+    //  normals -- a later CLOSEST_PLANE_SIMPLE / NAPX match or a download sees what the reference's scan holds)
+    double tinv[16], alignxf[16];
     if (!b200icp_m4inv(T, tinv)) return b200icp_set_error_(B200ICP_ESTATE, "lum_solve_update: singular transMat");
     b200icp_euler_to_matrix4(nPos, nTh, alignxf);
-    b200icp_mmult(tinv, T, t1);
-    b200icp_mmult(alignxf, t1, t2);
-    memcpy(T, t2, sizeof T);
-    b200icp_mmult(tinv, dal, t1);
-    b200icp_mmult(alignxf, t1, t2);
-    memcpy(dal, t2, sizeof dal);
-    b200icp_scan_set_pose(scans[i], T, dal);
+    b200icp_scan_transform(scans[i], tinv);
+    b200icp_scan_transform(scans[i], alignxf);
     if (frames) {   // transformToEuler(.., Scan::LUM, i != last ? 1 : 2), lum6Deuler.cc:447-451
       std::vector<double> all((size_t)16 * n_scans);
       for (int k = 0; k < n_scans; ++k) b200icp_scan_get_pose(scans[k], &all[(size_t)16 * k], nullptr);
