@@ -931,8 +931,8 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   return B200ICP_OK;
 }
 
-#ifdef B200_TILE_STATS
-// debug builds only: counters of the cooperative tile search (batches tiled, staged points, batches refused); reset on read
+#if defined(B200_TILE_STATS) || defined(B200_COUNT_UNSETTLED)
+// debug builds only: counters of the cooperative tile search (or, with B200_COUNT_UNSETTLED, of the fp32-ambiguous searches) (batches tiled, staged points, batches refused); reset on read
 int b200icp_debug_tile_stats(unsigned long long* out8) {
   unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpyFromSymbol(out8, g_tile_stats, sizeof z) != cudaSuccess) return -1;
@@ -944,6 +944,10 @@ int b200icp_debug_tile_stats(unsigned long long* out8) {
 // debug builds only: per-block (start, tile loop done, partials stored, SM id) of the last fused iteration launch
 int b200icp_debug_blocks(unsigned long long* out, int nblocks) {
   return cudaMemcpyFromSymbol(out, g_blk, (size_t)nblocks * 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+// debug builds only: per-warp (walk start, walk end, leftover start, leftover end, search batches, -) of the last launch
+int b200icp_debug_warps(unsigned long long* out, int nblocks) {
+  return cudaMemcpyFromSymbol(out, g_wrp, (size_t)nblocks * 48 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
 }
 // debug builds only: the in-kernel timeline of the last iteration (globaltimer ns), see tl_mark
 int b200icp_debug_timing(unsigned long long* out32) {

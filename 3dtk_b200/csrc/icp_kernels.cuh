@@ -30,15 +30,31 @@ __device__ __forceinline__ void blk_mark(int k) {
     if (k == 0) { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); g_blk[blockIdx.x][3] = s; }
   }
 }
+// per-warp record of the fused iteration kernel: [block][warp][0..5] = walk start, walk end (before the block
+// barrier), leftover batches start, leftover batches end, search batches run by the warp, (unused)
+__device__ unsigned long long g_wrp[2048][8][6];
+__device__ __forceinline__ void wrp_mark(int k) {
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 2048) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_wrp[blockIdx.x][threadIdx.x >> 5][k] = t;
+  }
+}
+__device__ __forceinline__ void wrp_count(int k, bool reset) {
+  if ((threadIdx.x & 31) == 0 && blockIdx.x < 2048) {
+    if (reset) g_wrp[blockIdx.x][threadIdx.x >> 5][k] = 0; else g_wrp[blockIdx.x][threadIdx.x >> 5][k] += 1;
+  }
+}
 #else
 __device__ __forceinline__ void tl_mark(int) {}
 __device__ __forceinline__ void blk_mark(int) {}
+__device__ __forceinline__ void wrp_mark(int) {}
+__device__ __forceinline__ void wrp_count(int, bool) {}
 #endif
 
 struct XfSmem {
   double X[16], Sinv[16], S[16], Nm[9], o[3];
   float dX[12];     // X - Xprev (rotation block + translation), fp32: per-iteration motion of a data point
   float dXabs;      // max |entry| of the rotation block of dX (rounding bound)
+  int need_dd;      // the running minimizer reads the MP_DD moments (HELIX, APX); the others skip their 6 sums
 };
 
 __device__ __forceinline__ void xf_apply(const double* M, double x, double y, double z, double& ox,
@@ -117,6 +133,7 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
                                                   unsigned* __restrict__ stage2_log,
                                                   unsigned* __restrict__ stage2_counter) {
   // ---- icp6D::match loop body after getPtPairs (icp6D.cc:124-125, :229-279)
+  tl_mark(20);
   const int iter = st->iter;
   st->prev_prev_ret = st->prev_ret;
   st->prev_ret = st->ret;
@@ -128,9 +145,11 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
     st->ret_iter = iter;
     return;
   }
+  tl_mark(21);
   double alignxf[16];
   for (int i = 0; i < 16; ++i) alignxf[i] = st->alignxf[i];  // kept when the Cholesky path bails out
   const double ret = solve_any(st->algo, mom, st->o, st->napx_weighted, alignxf);
+  tl_mark(22);
   st->ret = ret;
   for (int i = 0; i < 16; ++i) st->alignxf[i] = alignxf[i];
   rms_log[st->iters_run] = ret;
@@ -139,6 +158,7 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
   stage2_log[2 * st->iters_run + 1] = searches_now;
   st->iters_run += 1;
   // Scan::transformMatrix (scan.cc:878-898): transMat <- alignxf*transMat, dalignxf <- alignxf*dalignxf
+  tl_mark(23);
   double tmp[16];
   m4_mul(alignxf, st->X, tmp);
   for (int i = 0; i < 16; ++i) { st->Xprev[i] = st->X[i]; st->X[i] = tmp[i]; }
@@ -154,6 +174,7 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
       nn[3 * r + c] = alignxf[4 * r + 0] * st->Nm[c] + alignxf[4 * r + 1] * st->Nm[3 + c] +
                       alignxf[4 * r + 2] * st->Nm[6 + c];
   for (int i = 0; i < 9; ++i) st->Nm[i] = nn[i];
+  tl_mark(24);
   if ((fabs(ret - st->prev_ret) < st->eps && fabs(ret - st->prev_prev_ret) < st->eps) ||
       iter == st->max_iter - 1) {
     st->done = 1;
@@ -188,12 +209,24 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
   tl_mark(9);
   // reduction: lane = moment, warp w takes blocks w, w+8, ... -> every load is one coalesced 184/352-byte row
   // of a block's partials; fixed shape, so the sums do not depend on timing
+  // (groups of 16 predicated loads, all in flight together, no remainder loop: a rolled remainder exposes one L2
+  //  round trip per block on the serial tail of the iteration -- 5.4 -> 3.5 us measured)
+  constexpr int kRedGroup = 16;
+  const int trips = (nblocks - warp + kWarps - 1) / kWarps;   // blocks this warp sums: warp, warp + 8, ...
   for (int k0 = 0; k0 < NS; k0 += 32) {
     const int k = k0 + lane;
     double v = 0.0;
     if (k < NS) {
-#pragma unroll 24   // the loads are independent: keep many in flight, this sits on the serial tail of the iteration
-      for (int b = warp; b < nblocks; b += kWarps) v += __ldcg(partials + (size_t)b * NS_MAX + k);
+      for (int j0 = 0; j0 < trips; j0 += kRedGroup) {
+        double x[kRedGroup];
+#pragma unroll
+        for (int u = 0; u < kRedGroup; ++u) {
+          const int b = warp + (j0 + u) * kWarps;
+          x[u] = b < nblocks ? __ldcg(partials + (size_t)b * NS_MAX + k) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRedGroup; ++u) v += x[u];
+      }
       wpart[warp][k] = v;
     }
   }
@@ -297,7 +330,7 @@ __device__ __forceinline__ void accumulate_pair_pt(const PairCtx& pc, Acc&& acc,
     p1[2] = nv[2] * dot + p2[2];
   }
   if (NAPX) accumulate_napx(acc, p1, p2, nv, xf.o);
-  else accumulate_p2p(acc, p1, p2, xf.o);
+  else accumulate_p2p(acc, p1, p2, xf.o, xf.need_dd != 0);
 }
 
 template <bool NAPX, bool PLANE, class Acc>
@@ -353,6 +386,7 @@ __device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict_
     const int k = tid - 32, c = k / 3, r = k % 3;
     xf.dX[k] = (float)(st->X[4 * c + r] - st->Xprev[4 * c + r]);
   }
+  if (tid == 65) xf.need_dd = algo_needs_dd(st->algo) ? 1 : 0;
   if (tid == 64) {
     double m = 0.0;
     for (int c = 0; c < 3; ++c)
@@ -403,6 +437,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
 
   // full search of up to 32 queued queries (list[0..nb)), one per lane
   auto run_batch = [&](const int* list, int nb) {
+    wrp_count(4, false);
     const bool on = lane < nb;
     uint32_t i = 0;
     double tx = 0, ty = 0, tz = 0, sx = 0, sy = 0, sz = 0;
@@ -430,6 +465,8 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   };
 
   const uint32_t ntiles = (nd + kBlock - 1) / kBlock;
+  wrp_count(4, true);
+  wrp_mark(0);
   // streaming part of one query: skip path inline, otherwise report "needs a search"
   auto stream_one = [&](uint32_t i, bool active) -> bool {
     if (rnd > 1 && active) active = (hash32(i ^ iter_salt) % (unsigned)rnd) == 0u;
@@ -496,6 +533,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     enqueue(i, stream_one(i, i < nd));
   }
 #endif
+  wrp_mark(1);
   // leftovers: merge the warps' partial queues so the remaining searches run in full batches
   if (lane == 0) sm.left_count[warp] = qcount;
   __syncthreads();
@@ -510,8 +548,10 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     }
     if (lane < qcount) sm.leftover[off + lane] = queue[lane];
     __syncthreads();
+    wrp_mark(2);
     for (int base = warp * 32; base < total; base += kWarps * 32)
       run_batch(sm.leftover + base, min(32, total - base));
+    wrp_mark(3);
   }
 
   block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);

@@ -784,6 +784,9 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool ac
         // certified radius: the requested ball, or better the (de-inflated) reach of the scanned cells
         rcert2 = fmaxf(__double2float_rd(rs2), rc2 * 0.99999f - 2e-6f * hh);
         settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
+#ifdef B200_COUNT_UNSETTLED   // debug counters, tools/unsettled_stats.py
+        if (!settled) atomicAdd(&g_tile_stats[0], 1ull);
+#endif
         if (!settled) {  // rare: two contenders closer than the fp32 error -> settle in fp64
           b.thr = filter_bound<true>(b.d2, e);
           for (int k = 0; k < nrows; ++k)
@@ -805,8 +808,15 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool ac
           const double cv = (double)kmax * g.h;
           need2 = !(b.j >= 0 && b.d2 <= cv * cv * (1.0 - 1e-9));
         }
+#ifdef B200_COUNT_UNSETTLED
+        if (!settled) atomicAdd(&g_tile_stats[1], 1ull);
+#endif
       }
       if (settled && !need2) budget_out = motion_budget(b, c, e, rcert2, maxdist2);
+#ifdef B200_COUNT_UNSETTLED
+      if (settled && !need2 && budget_out < 2e-3f) atomicAdd(&g_tile_stats[2], 1ull);
+      if (settled && !need2 && budget_out < 2e-4f) atomicAdd(&g_tile_stats[3], 1ull);
+#endif
     } else {
       // farther than maxdist from the model's bounding box: nothing can pair until it comes closer
       const double slack = sqrt(dbox2) * (1.0 - 1e-9) - sqrt(maxdist2) * (1.0 + 1e-12);

@@ -660,8 +660,9 @@ B2_HD double solve_any(int algo, const double* mom, const double* o, int napx_we
 }
 
 // Per-pair accumulation, shared by the host path (b200icp_align_pairs) and the kernels.
+// dd: also sum p2' p2'^T (MP_DD) -- only the HELIX and APX minimizers read it
 template <class Acc>
-B2_HD void accumulate_p2p(Acc&& acc, const double* p1, const double* p2, const double* o) {
+B2_HD void accumulate_p2p(Acc&& acc, const double* p1, const double* p2, const double* o, bool dd = true) {
   double a[3] = {p1[0] - o[0], p1[1] - o[1], p1[2] - o[2]};
   double b[3] = {p2[0] - o[0], p2[1] - o[1], p2[2] - o[2]};
   double e0 = p1[0] - p2[0], e1 = p1[1] - p2[1], e2 = p1[2] - p2[2];
@@ -670,9 +671,14 @@ B2_HD void accumulate_p2p(Acc&& acc, const double* p1, const double* p2, const d
   for (int i = 0; i < 3; ++i) { acc[MP_M + i] += a[i]; acc[MP_D + i] += b[i]; }
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) acc[MP_DM + 3 * i + j] += b[i] * a[j];
-  acc[MP_DD + 0] += b[0] * b[0]; acc[MP_DD + 1] += b[0] * b[1]; acc[MP_DD + 2] += b[0] * b[2];
-  acc[MP_DD + 3] += b[1] * b[1]; acc[MP_DD + 4] += b[1] * b[2]; acc[MP_DD + 5] += b[2] * b[2];
+  if (dd) {
+    acc[MP_DD + 0] += b[0] * b[0]; acc[MP_DD + 1] += b[0] * b[1]; acc[MP_DD + 2] += b[0] * b[2];
+    acc[MP_DD + 3] += b[1] * b[1]; acc[MP_DD + 4] += b[1] * b[2]; acc[MP_DD + 5] += b[2] * b[2];
+  }
 }
+
+// minimizers whose solve reads MP_DD
+B2_HD bool algo_needs_dd(int algo) { return algo == 5 || algo == 6; }
 
 template <class Acc>
 B2_HD void accumulate_napx(Acc&& acc, const double* p1, const double* p2, const double* nrm,

@@ -22,9 +22,10 @@ icp.lib.b200icp_debug_timing(t)
 names = {16: "stream: block0 start", 17: "stream: after pdl_wait", 18: "stream: block0 tiles done", 19: "stream: block0 reduced",
          0: "search: block0 start", 1: "search: after pdl_wait", 2: "search: prologue done", 3: "search: block0 batches done",
          4: "search: block0 partials stored", 7: "last block: ticket won", 8: "solve: start", 9: "solve: state staged",
-         10: "solve: moments reduced", 11: "solve: serial solve done", 12: "solve: state written"}
-order = [16, 17, 18, 19, 0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 12]
-t0 = t[16]
+         10: "solve: moments reduced", 20: "serial: start", 21: "serial: counters exchanged", 22: "serial: solve_any done",
+         23: "serial: logs written", 24: "serial: poses composed", 11: "solve: serial solve done", 12: "solve: state written"}
+order = [8, 9, 10, 20, 21, 22, 23, 24, 11, 12]
+t0 = t[8]
 print("n=%d iterations_run=%d  (ns since the stream kernel's block 0 started, last iteration)" % (n, r["iterations_run"]))
 for k in order:
     print("%8d  %s" % (t[k] - t0, names[k]))
