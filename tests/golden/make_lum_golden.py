@@ -3,8 +3,8 @@
 (oracle/_ref/libref3dtk.so, built from /root/reference by oracle/Makefile).  Run in the build container:
     python tests/golden/make_lum_golden.py      -> tests/golden/lum_vectors.npz
 Contents: Matrix4ToEuler (globals.icc:540-578) on poses covering both asin branches and the gimbal-lock branch.
-lum6Deuler.cc / graph.cc themselves do not compile here (CXSparse, boost::graph), so no reference outputs exist
-for doGraphSlam6D or Graph(): those are checked against oracle/oracle_icp.cpp only (parity unpinned there)."""
+doGraphSlam6D, covarianceEuler / covarianceQuat and Graph() are pinned separately, by the reference's own classes
+(tests/golden/make_full_golden.py, oracle/_ref/libref3dtk_full.so)."""
 import os, sys
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
