@@ -184,6 +184,193 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
   }
 }
 
+// ---- the same serial part on the 32 lanes of one warp, for icp6D_QUAT (the default minimizer) -------------------
+// One thread running solve_quat inside this kernel inherits its 80-register budget: the 4x4 work arrays go to local
+// memory and the solve takes 4.6 us against 1.8 us in a kernel of its own (tools/bench_src/solve_bench.cu), on the
+// serial tail of EVERY iteration.  Here the small dense pieces are spread over lanes instead: the 3x3 S, Horn's 4x4 Q,
+// the characteristic quartic from Q's principal minors (x^4 - e1 x^3 + e2 x^2 - e3 x + e4), the adjugate of
+// Q - lambda I (16 cofactors, one per lane), R, t and the two pose compositions; only Newton's iteration for lambda_max
+// stays serial (every lane runs it redundantly).  Same formulas as solve_quat / sym4_max_eigvec up to the order of a
+// few additions (1e-16 relative); w: >= 80 doubles of shared memory.
+__device__ __forceinline__ double det3_of(const double* A, int r0, int r1, int r2, int c0, int c1, int c2) {
+  return det3(A[4 * r0 + c0], A[4 * r0 + c1], A[4 * r0 + c2], A[4 * r1 + c0], A[4 * r1 + c1], A[4 * r1 + c2],
+              A[4 * r2 + c0], A[4 * r2 + c1], A[4 * r2 + c2]);
+}
+// cofactor (r, c) of the 4x4 row-major A
+__device__ __forceinline__ double cof4(const double* A, int r, int c) {
+  const int r0 = r == 0 ? 1 : 0, r1 = r <= 1 ? 2 : 1, r2 = r <= 2 ? 3 : 2;
+  const int c0 = c == 0 ? 1 : 0, c1 = c <= 1 ? 2 : 1, c2 = c <= 2 ? 3 : 2;
+  const double d = det3_of(A, r0, r1, r2, c0, c1, c2);
+  return ((r + c) & 1) ? -d : d;
+}
+
+__device__ __forceinline__ double solve_quat_warp(const double* __restrict__ mom, const double* __restrict__ o,
+                                                  double* __restrict__ alignxf, double* __restrict__ w) {
+  const int lane = threadIdx.x & 31;
+  double* S = w;          // [9]  centred cross-covariance / n
+  double* Q = w + 16;     // [16] Horn's N, row-major
+  double* A = w + 32;     // [16] Q - lambda I
+  double* C = w + 48;     // [16] cofactors of A
+  double* term = w + 64;  // [16] principal minors of Q
+  const double n = mom[MP_N];
+  const double inv = 1.0 / n;
+  const double cm[3] = {mom[MP_M] * inv, mom[MP_M + 1] * inv, mom[MP_M + 2] * inv};
+  const double cd[3] = {mom[MP_D] * inv, mom[MP_D + 1] * inv, mom[MP_D + 2] * inv};
+  if (lane < 9) S[lane] = mom[MP_DM + lane] * inv - cd[lane / 3] * cm[lane % 3];
+  __syncwarp();
+  if (lane < 16) {
+    const int i = lane >> 2, j = lane & 3;
+    const double trace = S[0] + S[4] + S[8];
+    double q;
+    if (i == 0 && j == 0) q = trace;
+    else if (i == 0 || j == 0) {
+      const int k = i + j;   // 1, 2, 3 -> S12 - S21, S20 - S02, S01 - S10
+      q = k == 1 ? S[5] - S[7] : (k == 2 ? S[6] - S[2] : S[1] - S[3]);
+    } else {
+      q = S[3 * (i - 1) + (j - 1)] + S[3 * (j - 1) + (i - 1)] - (i == j ? trace : 0.0);
+    }
+    Q[lane] = q;
+  }
+  __syncwarp();
+  // coefficients: e2 = sum of the 6 principal 2x2 minors, e3 = sum of the 4 principal 3x3 minors, e4 = det Q
+  {
+    double t = 0.0;
+    if (lane < 6) {
+      const int i = lane < 3 ? 0 : (lane < 5 ? 1 : 2), j = lane < 3 ? lane + 1 : (lane < 5 ? lane - 1 : 3);
+      t = Q[5 * i] * Q[5 * j] - Q[4 * i + j] * Q[4 * j + i];
+    } else if (lane < 10) {
+      t = cof4(Q, lane - 6, lane - 6);
+    } else if (lane < 14) {
+      t = Q[lane - 10] * cof4(Q, 0, lane - 10);
+    }
+    if (lane < 14) term[lane] = t;
+  }
+  __syncwarp();
+  double fro = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) fro += Q[k] * Q[k];
+  const double e1 = (Q[0] + Q[5]) + (Q[10] + Q[15]);
+  const double e2 = ((term[0] + term[1]) + (term[2] + term[3])) + (term[4] + term[5]);
+  const double e3 = (term[6] + term[7]) + (term[8] + term[9]);
+  const double e4 = (term[10] + term[11]) + (term[12] + term[13]);
+  const double c1 = -e1, c2 = e2, c3 = -e3, c4 = e4;
+  double x = sqrt(fro) * (1.0 + 1e-12) + 1e-300;   // >= spectral radius >= lambda_max (as sym4_max_eigvec)
+  for (int it = 0; it < 100; ++it) {
+    const double p = (((x + c1) * x + c2) * x + c3) * x + c4;
+    const double dp = ((4.0 * x + 3.0 * c1) * x + 2.0 * c2) * x + c3;
+    if (!(dp > 0.0)) break;
+    const double xn = x - p / dp;
+    if (!(xn < x)) break;
+    const bool tiny = (x - xn) <= 4e-16 * fabs(x);
+    x = xn;
+    if (tiny) break;
+  }
+  if (lane < 16) A[lane] = Q[lane] - ((lane >> 2) == (lane & 3) ? x : 0.0);
+  __syncwarp();
+  if (lane < 16) C[lane] = cof4(A, lane >> 2, lane & 3);
+  __syncwarp();
+  int best = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (fabs(C[5 * i]) > fabs(C[5 * best])) best = i;
+  double q0 = C[best], q1 = C[4 + best], q2 = C[8 + best], q3 = C[12 + best];   // column `best` of the adjugate
+  const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+  if (!(n2 > 0.0)) { q0 = 1.0; q1 = q2 = q3 = 0.0; }
+  const double ql = 1.0 / sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+  q0 *= ql; q1 *= ql; q2 *= ql; q3 *= ql;
+  const double q00 = q0 * q0, q11 = q1 * q1, q22 = q2 * q2, q33 = q3 * q3;
+  const double q03 = q0 * q3, q13 = q1 * q3, q23 = q2 * q3, q02 = q0 * q2, q12 = q1 * q2, q01 = q0 * q1;
+  double R[3][3];
+  R[0][0] = q00 + q11 - q22 - q33;
+  R[1][1] = q00 - q11 + q22 - q33;
+  R[2][2] = q00 - q11 - q22 + q33;
+  R[0][1] = 2.0 * (q12 - q03);
+  R[1][0] = 2.0 * (q12 + q03);
+  R[0][2] = 2.0 * (q13 + q02);
+  R[2][0] = 2.0 * (q13 - q02);
+  R[1][2] = 2.0 * (q23 - q01);
+  R[2][1] = 2.0 * (q23 + q01);
+  if (lane == 0) {
+    m4_identity(alignxf);
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) alignxf[4 * c + r] = R[r][c];
+    const double cmo[3] = {cm[0] + o[0], cm[1] + o[1], cm[2] + o[2]};
+    const double cdo[3] = {cd[0] + o[0], cd[1] + o[1], cd[2] + o[2]};
+    set_translation_from_centroids(alignxf, cmo, cdo);
+  }
+  __syncwarp();
+  return sqrt(mom[MP_D2] * inv);
+}
+
+// solve_step_serial for icp6D_QUAT, run by ALL lanes of warp 0
+__device__ __forceinline__ void solve_step_quat_warp(IterState* st, const double* mom, double* __restrict__ rms_log,
+                                                     unsigned long long* __restrict__ npairs_log,
+                                                     unsigned* __restrict__ stage2_log,
+                                                     unsigned* __restrict__ stage2_counter, double* __restrict__ w) {
+  const int lane = threadIdx.x & 31;
+  tl_mark(20);
+  const int iter = st->iter;
+  const double prev_ret = st->ret, prev_prev_ret = st->prev_ret;
+  unsigned searches_now = 0;
+  __syncwarp();
+  if (lane == 0) {
+    st->prev_prev_ret = prev_prev_ret;
+    st->prev_ret = prev_ret;
+    st->stage2_last = atomicExch(stage2_counter, 0u);
+    searches_now = atomicExch(stage2_counter + 1, 0u);
+  }
+  const double np = mom[0];
+  if (!(np > 3.0)) {  // "do we have enough point pairs?" -> break before any transform
+    if (lane == 0) { st->done = 1; st->ret_iter = iter; }
+    return;
+  }
+  tl_mark(21);
+  const double ret = solve_quat_warp(mom, st->o, st->alignxf, w);
+  tl_mark(22);
+  const int run = st->iters_run;
+  __syncwarp();
+  if (lane == 0) {
+    st->ret = ret;
+    rms_log[run] = ret;
+    npairs_log[run] = (unsigned long long)(np + 0.5);
+    stage2_log[2 * run] = st->stage2_last;
+    stage2_log[2 * run + 1] = searches_now;
+    st->iters_run = run + 1;
+  }
+  tl_mark(23);
+  // Scan::transformMatrix (scan.cc:878-898): lanes 0-15 X <- alignxf*X, lanes 16-31 T <- alignxf*T (one entry each,
+  // MMult's operand order)
+  {
+    const double* A = st->alignxf;
+    const double* B = lane < 16 ? st->X : st->T;
+    const int e = lane & 15, r = e & 3, c = e >> 2;
+    const double v = A[r] * B[4 * c] + A[r + 4] * B[4 * c + 1] + A[r + 8] * B[4 * c + 2] + A[r + 12] * B[4 * c + 3];
+    // transform3normal (globals.icc:1465-1475): Nm <- R^T Nm
+    double nv = 0.0;
+    if (lane < 9) {
+      const int nr = lane / 3, nc = lane % 3;
+      nv = A[4 * nr + 0] * st->Nm[nc] + A[4 * nr + 1] * st->Nm[3 + nc] + A[4 * nr + 2] * st->Nm[6 + nc];
+    }
+    __syncwarp();
+    if (lane < 16) { st->Xprev[e] = st->X[e]; st->X[e] = v; }
+    else {
+      st->T[e] = v;
+      if (st->pose_log) st->pose_log[16 * run + e] = v;
+    }
+    if (lane < 9) st->Nm[lane] = nv;
+  }
+  tl_mark(24);
+  if (lane == 0) {
+    if ((fabs(ret - prev_ret) < st->eps && fabs(ret - prev_prev_ret) < st->eps) || iter == st->max_iter - 1) {
+      st->done = 1;
+      st->ret_iter = iter;
+    } else {
+      st->iter = iter + 1;
+    }
+  }
+  __syncwarp();
+}
+
 __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const double* __restrict__ partials,
                                         int nblocks, double* __restrict__ rms_log,
                                         unsigned long long* __restrict__ npairs_log,
@@ -196,7 +383,8 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
   constexpr int kWords = (int)(sizeof(IterState) / 8);
   double (*wpart)[NS_MAX] = reinterpret_cast<double (*)[NS_MAX]>(scratch);
   double* mom = scratch + kWarps * NS_MAX;
-  double* st_raw = mom + NS_MAX;
+  double* wq = mom + NS_MAX;          // 80 doubles of work space for the warp-parallel QUAT solve
+  double* st_raw = wq + 80;
   IterState* st = reinterpret_cast<IterState*>(st_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // stage the loop state in shared memory: one coalesced read now, one coalesced write at the end, instead
@@ -272,7 +460,12 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
       mom[tid] = t;
     }
     __syncthreads();
-    if (tid == 0 && comm_ok) solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
+    if (comm_ok) {
+      if (st->algo == 1) { if (warp == 0) solve_step_quat_warp(st, mom, rms_log, npairs_log, stage2_log, stage2_counter, wq); }
+      else if (tid == 0) solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
+    }
+  } else if (st->algo == 1) {
+    if (warp == 0) solve_step_quat_warp(st, mom, rms_log, npairs_log, stage2_log, stage2_counter, wq);
   } else if (tid == 0) {
     solve_step_serial(st, mom, rms_log, npairs_log, stage2_log, stage2_counter);
   }
