@@ -742,12 +742,30 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     if (lane < qcount) sm.leftover[off + lane] = queue[lane];
     __syncthreads();
     wrp_mark(2);
-    for (int base = warp * 32; base < total; base += kWarps * 32)
-      run_batch(sm.leftover + base, min(32, total - base));
+    // total < kWarps * 32 (every warp kept fewer than 32).  The remaining searches are spread over ALL warps: a
+    // batch lasts as long as its slowest lane, and the block waits for its slowest batch, so eight batches of 12
+    // finish earlier than three of 32 while five warps idle (late iterations: ~90 searches per block).
+    {
+      const int per = (total + kWarps - 1) / kWarps;
+      const int base = warp * per;
+      if (base < total) run_batch(sm.leftover + base, min(per, total - base));
+    }
     wrp_mark(3);
   }
 
-  block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+  // block sums of the NS accumulator columns: warp w takes moments w, w + 8, ...; a lane adds 8 of the column's 256
+  // thread entries, five shuffle steps finish it -- 3 x (8 loads + 10 shuffles) per warp instead of NS x 10 shuffles,
+  // fixed order
+  __syncthreads();
+  for (int k = warp; k < NS; k += kWarps) {
+    const double* col = &sm.acc[k][0];
+    double v = 0.0;
+#pragma unroll
+    for (int u = 0; u < kBlock / 32; ++u) v += col[u * 32 + lane];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) partials[(size_t)blockIdx.x * NS_MAX + k] = v;
+  }
   blk_mark(2);
   if (lane == 0 && stage2) atomicAdd(stage2_counter, stage2);
   if (lane == 0 && searches) atomicAdd(stage2_counter + 1, searches);
