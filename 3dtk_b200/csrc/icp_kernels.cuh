@@ -12,6 +12,7 @@
 //                     convergence test of icp6D::match (icp6D.cc:266-279), all in fp64 on device.
 //   nn_batch_kernel   SearchTree::getPtPairs for caller-supplied queries (API path).
 #pragma once
+#include <type_traits>
 #include "nn_search.cuh"
 
 namespace b200 {
@@ -588,6 +589,9 @@ __device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict_
   }
 }
 
+#ifndef B200_LEFT_SCAN_BATCH
+#define B200_LEFT_SCAN_BATCH 4   // candidate loads in flight per lane in the leftover batches (2: 7.60, 4: 7.56 ms)
+#endif
 #ifndef B200_DUAL_TILE
 #define B200_DUAL_TILE 0
 #endif
@@ -629,7 +633,10 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   int* queue = sm.queue[warp];
 
   // full search of up to 32 queued queries (list[0..nb)), one per lane
-  auto run_batch = [&](const int* list, int nb) {
+  // tag: std::integral_constant<int, 0> = batch inside the walk, <int, 1> = leftover batch after it (four candidate
+  // loads in flight per lane instead of two: latency matters there, not registers or issue slots)
+  auto run_batch = [&](const int* list, int nb, auto tag) {
+    constexpr bool kLeft = decltype(tag)::value != 0;
     wrp_count(4, false);
     const bool on = lane < nb;
     uint32_t i = 0;
@@ -647,8 +654,8 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     float newbud;
     // neighbours in the data scan's cell order -> overlapping stencils -> cooperative tile search
     const bool dense = nb == 32 && (unsigned)(list[31] - list[0]) <= (unsigned)kTileSpan;
-    nn_warp_search<EXACT>(model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2,
-                          dense);
+    nn_warp_search<EXACT, kLeft ? B200_LEFT_SCAN_BATCH : kScanBatch>(
+        model, sm.search, on, sx, sy, sz, maxdist2, seed, delta, bj, bd2, boidx, newbud, stage2, dense);
     if (on) {
       nn_cache[i] = bj;
       nn_budget[i] = newbud;
@@ -692,7 +699,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
       qcount += __popc(smask);
       if (lane == 0) searches += __popc(smask);
       __syncwarp();
-      if (qcount >= 32) { qcount -= 32; run_batch(queue + qcount, 32); }
+      if (qcount >= 32) { qcount -= 32; run_batch(queue + qcount, 32, std::integral_constant<int, 0>{}); }
     }
   };
 #if B200_DUAL_TILE
@@ -748,7 +755,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     {
       const int per = (total + kWarps - 1) / kWarps;
       const int base = warp * per;
-      if (base < total) run_batch(sm.leftover + base, min(per, total - base));
+      if (base < total) run_batch(sm.leftover + base, min(per, total - base), std::integral_constant<int, 1>{});
     }
     wrp_mark(3);
   }

@@ -177,16 +177,16 @@ __device__ __forceinline__ void best_merge(Best& b, double od2, int oj, unsigned
 // flattened fp32 scan of the first `nrows` ranges of this thread's table.  Candidates are taken four at
 // a time: their indices come from the (cheap) range walk, then four independent 16-byte loads are in
 // flight before the first distance is needed -- the loop is bound by load latency, not arithmetic.
-template <class SM>
+template <int SB = kScanBatch, class SM>
 __device__ __forceinline__ void scan_rows(const GridDev& g, const SM& sm, int nrows, float qx,
                                           float qy, float qz, Cand& c) {
   const int tid = threadIdx.x;
   int r = 0;
   unsigned j = 0, end = 0;
   for (;;) {
-    int idx[kScanBatch];
+    int idx[SB];
 #pragma unroll
-    for (int u = 0; u < kScanBatch; ++u) {
+    for (int u = 0; u < SB; ++u) {
       while (j >= end && r < nrows) {
         j = sm.rng[2 * r][tid];
         end = sm.rng[2 * r + 1][tid];
@@ -195,12 +195,12 @@ __device__ __forceinline__ void scan_rows(const GridDev& g, const SM& sm, int nr
       idx[u] = j < end ? (int)j++ : -1;
     }
     if (idx[0] < 0) break;
-    float4 p[kScanBatch];
+    float4 p[SB];
 #pragma unroll
-    for (int u = 0; u < kScanBatch; ++u)
+    for (int u = 0; u < SB; ++u)
       if (idx[u] >= 0) p[u] = __ldg(g.p32 + idx[u]);
 #pragma unroll
-    for (int u = 0; u < kScanBatch; ++u)
+    for (int u = 0; u < SB; ++u)
       if (idx[u] >= 0 && idx[u] != c.j1)   // a point met twice must not become its own runner-up
         cand_update(c, dist32(p[u], qx, qy, qz), idx[u]);
   }
@@ -268,7 +268,9 @@ __device__ __forceinline__ void stencil_ranges(const GridDev& g, int cx, int cy,
 
 // fp32 scan of those runs by the query's own thread.  Leaves the non-empty ranges in the thread's table
 // (`nrows` of them) and the tracking state in `c` (seeded with b's point).
-template <class SM>
+// (tried for the leftover batches: prefetch.global.L1 of the runs' cache lines as soon as the runs are known --
+//  7.65 vs 7.60 ms per match, slower)
+template <int SB = kScanBatch, class SM>
 __device__ __forceinline__ int stencil_scan(const GridDev& g, SM& sm, int cx, int cy, int cz,
                                             float fx, float fy, float fz, float qx, float qy, float qz,
                                             float r2, const Best& b, Cand& c, float& rc2) {
@@ -284,7 +286,7 @@ __device__ __forceinline__ int stencil_scan(const GridDev& g, SM& sm, int cx, in
       ++nrows;
     }
   cand_seed(g, b, qx, qy, qz, c);
-  scan_rows(g, sm, nrows, qx, qy, qz, c);
+  scan_rows<SB>(g, sm, nrows, qx, qy, qz, c);
   return nrows;
 }
 
@@ -378,7 +380,7 @@ __device__ __forceinline__ float slab_dist(int d, float f, float h) {
 // Thread-level fp32 scan of a ball wider than a cell: covers the cells within `kmax` (<= kBallRings) of
 // the query's cell.  r2 = initial squared search radius (inflated); the ball shrinks to
 // (dist(best) + 2*delta)^2 as candidates appear.  On return r2 is the final (inflated) radius.
-template <class SM>
+template <int SB = kScanBatch, class SM>
 __device__ __forceinline__ void ball_scan(const GridDev& g, SM& sm, int cx, int cy, int cz, float fx,
                                           float fy, float fz, float qx, float qy, float qz, float e,
                                           float delta, int kmax, const Best& b, float& r2, Cand& c) {
@@ -438,7 +440,7 @@ __device__ __forceinline__ void ball_scan(const GridDev& g, SM& sm, int cx, int 
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (k < n) { sm.rng[2 * k][tid] = va[k]; sm.rng[2 * k + 1][tid] = vb[k]; }
-    scan_rows(g, sm, n, qx, qy, qz, c);
+    scan_rows<SB>(g, sm, n, qx, qy, qz, c);
     // ---- shrink the ball to the (error-inflated) fp32 distance of the current best, plus the margin
     if (c.j1 >= 0) {
       const float rr = sqrtf(c.d1 + fp32_tol(c.d1, e)) * 1.00001f + 2.0f * delta;
@@ -732,7 +734,8 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool ac
 // collectives, no block barrier).  `active` lanes carry a query s (in the grid's frame); seed_j is the
 // sorted position of the neighbour found for this query last time (-1: none); delta >= 0 asks for a
 // motion budget (see header).  budget_out = certified budget (0 when none could be certified).
-template <bool EXACT, class SM>
+// SB: candidate loads kept in flight per lane
+template <bool EXACT, int SB = kScanBatch, class SM>
 __device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool active, double sx,
                                                double sy, double sz, double maxdist2, int seed_j,
                                                float delta, int& out_j, double& out_d2,
@@ -780,7 +783,7 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool ac
         // the ball fits inside the stencil's guaranteed radius: stage 1 alone is exact
         const float r2 = fminf(__double2float_ru(rs2), 3.0e38f) * 1.00001f + 1e-6f * hh;
         float rc2;
-        const int nrows = stencil_scan(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, r2, b, c, rc2);
+        const int nrows = stencil_scan<SB>(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, r2, b, c, rc2);
         // certified radius: the requested ball, or better the (de-inflated) reach of the scanned cells
         rcert2 = fmaxf(__double2float_rd(rs2), rc2 * 0.99999f - 2e-6f * hh);
         settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
@@ -798,7 +801,7 @@ __device__ __forceinline__ void nn_warp_search(const GridDev& g, SM& sm, bool ac
         const int kmax = (int)fmin(kneed, (double)kBallRings);
         float r2 = fminf(__double2float_ru(rs2), 3.0e38f) * 1.00001f + 1e-6f * hh;
         const Best seed = b;
-        ball_scan(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, e, delta, kmax, b, r2, c);
+        ball_scan<SB>(g, sm, cx, cy, cz, fx, fy, fz, qx, qy, qz, e, delta, kmax, b, r2, c);
         settled = finalize_cand<EXACT>(g, c, e, sx, sy, sz, b);
         // certified radius: the final ball, de-inflated, but never more than the scanned rings cover
         const float cover = (float)kmax * (float)g.h;
