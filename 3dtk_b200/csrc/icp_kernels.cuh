@@ -674,13 +674,16 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     if (active) {
       double tx, ty, tz, sx, sy, sz;
       float step, delta;
+      // (the cached neighbour's index is fetched together with the point and its budget, not after the budget test:
+      //  one dependent round trip less per trip of the walk)
+      const int seed = can_skip ? nn_cache[i] : -1;
+      const float bud0 = can_skip ? nn_budget[i] : 0.f;
       query_state(xf, dq, i, can_skip, dmin, dmax, tx, ty, tz, sx, sy, sz, step, delta);
-      const float bud = can_skip ? nn_budget[i] - step : 0.f;
+      const float bud = bud0 - step;
       search = !(bud > 0.f);
       if (!search) {
         // the cached neighbour is still THE nearest neighbour; only its distance is re-evaluated
         nn_budget[i] = bud;
-        const int seed = nn_cache[i];
         if (seed >= 0) {
           const double d2 = EXACT ? exact_d2(model, seed, sx, sy, sz)
                                   : (double)dist32(__ldg(model.p32 + seed), (float)(sx - model.c[0]),
