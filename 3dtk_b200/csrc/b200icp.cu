@@ -819,6 +819,32 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
   hs->napx_weighted = prm->napx_weighted;
   hs->max_iter = max_iter;
   hs->pose_log = ctx->pose_log.p;
+  // fixed-point scales of the point-to-point moment sums (FixAcc, icp_kernels.cuh).  Every addend is bounded through
+  // |p - o| <= R for both points of a pair (o = the model's bbox centre; a data point pairs only within maxdist of
+  // a model point) and |p1 - p2| < maxdist; R, D carry a factor 2 of head room.
+  {
+    double hd = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      const double e = 0.5 * (model->g.bbox_hi[k] - model->g.bbox_lo[k]);
+      hd += e * e;
+    }
+    const double md = prm->max_dist_match;
+    const double R = 2.0 * (std::sqrt(hd) + 2.0 * md) + 1.0, D = 2.0 * md + 1e-3;
+    double bound[NS_P2P];
+    for (int k = 0; k < NS_P2P; ++k) bound[k] = R * R;
+    bound[MP_N] = 2.0;
+    bound[MP_D2] = D * D;
+    for (int k = 0; k < 3; ++k) bound[MP_M + k] = bound[MP_D + k] = R;
+    for (int k = 0; k < NS_P2P; ++k) {
+      int ex = 0, ex1 = 0;
+      std::frexp(bound[k] * (double)std::max<size_t>(data->n, 1), &ex);   // nd * bound < 2^ex
+      std::frexp(bound[k], &ex1);                                          //      bound < 2^ex1
+      const int sh = std::min(60 - ex, 50 - ex1);    // totals below 2^60, every addend below 2^50 (FixRef)
+      hs->fix_s[k] = std::ldexp(1.0, sh);
+      hs->fix_inv[k] = std::ldexp(1.0, -sh);
+    }
+    hs->fixed_point = 1;
+  }
   CU_TRY(cudaMemcpyAsync(ctx->d_state.p, hs, sizeof(IterState), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(ctx->nn_cache.p, 0xFF, data->n * sizeof(int), st));  // -1: no cached neighbour
   CU_TRY(cudaMemsetAsync(ctx->nn_budget.p, 0, data->n * sizeof(float), st));

@@ -52,6 +52,11 @@ struct IterState {
   int napx_weighted;
   int max_iter;
   unsigned int stage2_last;
+  unsigned int searches_last;  // full searches of the previous iteration (picks the hand-out mode of the next launch)
+  int fixed_point;             // the launch's partial sums are fixed-point integers (point-to-point moment set)
+  // fixed-point scales of the point-to-point moment sums (powers of two, chosen per match from the scene's extent so
+  // that nd * max|addend| < 2^60) and their inverses, see FixAcc in icp_kernels.cuh
+  double fix_s[NS_P2P], fix_inv[NS_P2P];
   double* pose_log;   // [max_iter][16] transMat after every iteration that produced a transform (frames, see
                       // b200icp_last_poses); may be NULL
 };

@@ -56,6 +56,7 @@ struct XfSmem {
   float dX[12];     // X - Xprev (rotation block + translation), fp32: per-iteration motion of a data point
   float dXabs;      // max |entry| of the rotation block of dX (rounding bound)
   int need_dd;      // the running minimizer reads the MP_DD moments (HELIX, APX); the others skip their 6 sums
+  double fs[NS_P2P]; // fixed-point scales (accumulate_p2p_fix)
 };
 
 __device__ __forceinline__ void xf_apply(const double* M, double x, double y, double z, double& ox,
@@ -84,6 +85,43 @@ struct SmemAcc {
   double* base;
   __device__ __forceinline__ double& operator[](int k) const { return base[k * kBlock]; }
 };
+
+// Order-independent sums: the same thread-private columns, holding 64-bit integers.  A pair adds round(v * s[k]) to
+// column k; integer addition is associative, so the totals do not depend on which thread summed which pair, in
+// which order -- that is what lets the kernel hand the scan out dynamically and still return bit-identical results
+// from run to run.  s[k] is a power of two with nd * max|v| < 2^60 (b200icp_match); rounding < 0.5 / s[k] per pair,
+// unbiased: at 1M pairs the totals keep 13-14 digits, like the fp64 sums they replace.
+// The conversion is one fused multiply-add: v * s + 1.5 * 2^52 is rounded (to nearest) to an integer that sits in the
+// low mantissa bits, so the integer is the bit pattern minus the constant's -- no F2I, which costs the walk 35 % when
+// done 17 times per pair.  Needs |v * s| < 2^51 per addend; b200icp_match chooses s accordingly.
+constexpr double kFixMagic = 6755399441055744.0;                // 1.5 * 2^52
+constexpr long long kFixMagicBits = 0x4338000000000000LL;       // its bit pattern
+__device__ __forceinline__ void fix_add(long long* col, int k, double v, double s) {
+  col[k * kBlock] += __double_as_longlong(__fma_rn(v, s, kFixMagic)) - kFixMagicBits;
+}
+// accumulate_p2p (solve.h) on integer columns.  fs = the scales: one for the count, one for sum |p1 - p2|^2, one for
+// the first moments, one for the second moments (fs[MP_N], fs[MP_D2], fs[MP_M], fs[MP_DM]; MP_D = MP_M, MP_DD = MP_DM).
+// The data point is scaled once, so a second moment is one fma like in the fp64 version.
+__device__ __forceinline__ void accumulate_p2p_fix(long long* col, const double* __restrict__ fs, const double* p1,
+                                                   const double* p2, const double* o, bool dd) {
+  const double a[3] = {p1[0] - o[0], p1[1] - o[1], p1[2] - o[2]};
+  const double b[3] = {p2[0] - o[0], p2[1] - o[1], p2[2] - o[2]};
+  const double e0 = p1[0] - p2[0], e1 = p1[1] - p2[1], e2 = p1[2] - p2[2];
+  const double s1 = fs[MP_M], s2 = fs[MP_DM];
+  fix_add(col, MP_N, 1.0, fs[MP_N]);
+  fix_add(col, MP_D2, e0 * e0 + e1 * e1 + e2 * e2, fs[MP_D2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { fix_add(col, MP_M + i, a[i], s1); fix_add(col, MP_D + i, b[i], s1); }
+  const double bs[3] = {b[0] * s2, b[1] * s2, b[2] * s2};   // exact: s2 is a power of two
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) fix_add(col, MP_DM + 3 * i + j, bs[i], a[j]);
+  if (dd) {
+    fix_add(col, MP_DD + 0, bs[0], b[0]); fix_add(col, MP_DD + 1, bs[0], b[1]); fix_add(col, MP_DD + 2, bs[0], b[2]);
+    fix_add(col, MP_DD + 3, bs[1], b[1]); fix_add(col, MP_DD + 4, bs[1], b[2]); fix_add(col, MP_DD + 5, bs[2], b[2]);
+  }
+}
 
 template <int NS, class Acc>
 __device__ __forceinline__ void block_reduce_store(Acc acc, double* __restrict__ out) {
@@ -157,6 +195,7 @@ __device__ __forceinline__ void solve_step_serial(IterState* st, const double* m
   npairs_log[st->iters_run] = (unsigned long long)(np + 0.5);
   stage2_log[2 * st->iters_run] = st->stage2_last;
   stage2_log[2 * st->iters_run + 1] = searches_now;
+  st->searches_last = searches_now;
   st->iters_run += 1;
   // Scan::transformMatrix (scan.cc:878-898): transMat <- alignxf*transMat, dalignxf <- alignxf*dalignxf
   tl_mark(23);
@@ -336,6 +375,7 @@ __device__ __forceinline__ void solve_step_quat_warp(IterState* st, const double
     npairs_log[run] = (unsigned long long)(np + 0.5);
     stage2_log[2 * run] = st->stage2_last;
     stage2_log[2 * run + 1] = searches_now;
+    st->searches_last = searches_now;
     st->iters_run = run + 1;
   }
   tl_mark(23);
@@ -372,8 +412,9 @@ __device__ __forceinline__ void solve_step_quat_warp(IterState* st, const double
   __syncwarp();
 }
 
+// fixed: the partial rows hold 64-bit integers (accumulate_p2p_fix): summed exactly, then scaled back by fix_inv
 __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const double* __restrict__ partials,
-                                        int nblocks, double* __restrict__ rms_log,
+                                        int nblocks, bool fixed, double* __restrict__ rms_log,
                                         unsigned long long* __restrict__ npairs_log,
                                         unsigned* __restrict__ stage2_log,
                                         unsigned* __restrict__ stage2_counter, double* scratch,
@@ -413,16 +454,31 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
           const int b = warp + (j0 + u) * kWarps;
           x[u] = b < nblocks ? __ldcg(partials + (size_t)b * NS_MAX + k) : 0.0;
         }
+        if (fixed) {
+          long long iv = __double_as_longlong(v);
 #pragma unroll
-        for (int u = 0; u < kRedGroup; ++u) v += x[u];
+          for (int u = 0; u < kRedGroup; ++u) iv += __double_as_longlong(x[u]);
+          v = __longlong_as_double(iv);
+        } else {
+#pragma unroll
+          for (int u = 0; u < kRedGroup; ++u) v += x[u];
+        }
       }
       wpart[warp][k] = v;
     }
   }
   __syncthreads();
-  if (tid < NS)
-    mom[tid] = ((wpart[0][tid] + wpart[1][tid]) + (wpart[2][tid] + wpart[3][tid])) +
-               ((wpart[4][tid] + wpart[5][tid]) + (wpart[6][tid] + wpart[7][tid]));
+  if (tid < NS) {
+    if (fixed) {
+      long long iv = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) iv += __double_as_longlong(wpart[w][tid]);
+      mom[tid] = (double)iv * st->fix_inv[tid];
+    } else {
+      mom[tid] = ((wpart[0][tid] + wpart[1][tid]) + (wpart[2][tid] + wpart[3][tid])) +
+                 ((wpart[4][tid] + wpart[5][tid]) + (wpart[6][tid] + wpart[7][tid]));
+    }
+  }
   __syncthreads();
   tl_mark(10);
   if (comm.world > 1) {
@@ -502,7 +558,7 @@ struct PairCtx {   // everything needed to turn (query, neighbour) into moments
 
 // forms the pair of data point i (current position t, neighbour at sorted position bj) and accumulates it
 // (mx,my,mz) = the neighbour's coordinates in the model grid's frame (p64 of the model scan)
-template <bool NAPX, bool PLANE, class Acc>
+template <bool NAPX, bool PLANE, bool FIXP = false, class Acc>
 __device__ __forceinline__ void accumulate_pair_pt(const PairCtx& pc, Acc&& acc, uint32_t i, double mx, double my,
                                                    double mz, double tx, double ty, double tz) {
   const XfSmem& xf = *pc.xf;
@@ -523,16 +579,17 @@ __device__ __forceinline__ void accumulate_pair_pt(const PairCtx& pc, Acc&& acc,
     p1[1] = nv[1] * dot + p2[1];
     p1[2] = nv[2] * dot + p2[2];
   }
-  if (NAPX) accumulate_napx(acc, p1, p2, nv, xf.o);
+  if constexpr (NAPX) accumulate_napx(acc, p1, p2, nv, xf.o);
+  else if constexpr (FIXP) accumulate_p2p_fix(reinterpret_cast<long long*>(acc.base), xf.fs, p1, p2, xf.o, xf.need_dd != 0);
   else accumulate_p2p(acc, p1, p2, xf.o, xf.need_dd != 0);
 }
 
-template <bool NAPX, bool PLANE, class Acc>
+template <bool NAPX, bool PLANE, bool FIXP = false, class Acc>
 __device__ __forceinline__ void accumulate_pair(const PairCtx& pc, Acc&& acc, uint32_t i, int bj, double tx,
                                                 double ty, double tz) {
   const double2 pa = __ldg(reinterpret_cast<const double2*>(pc.model->p64 + bj));
   const double pz = __ldg(reinterpret_cast<const double*>(pc.model->p64 + bj) + 2);
-  accumulate_pair_pt<NAPX, PLANE>(pc, acc, i, pa.x, pa.y, pz, tx, ty, tz);
+  accumulate_pair_pt<NAPX, PLANE, FIXP>(pc, acc, i, pa.x, pa.y, pz, tx, ty, tz);
 }
 
 // current position of data point i, its position one iteration ago and the margin worth asking for
@@ -581,6 +638,7 @@ __device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict_
     xf.dX[k] = (float)(st->X[4 * c + r] - st->Xprev[4 * c + r]);
   }
   if (tid == 65) xf.need_dd = algo_needs_dd(st->algo) ? 1 : 0;
+  if (tid >= 128 && tid < 128 + NS_P2P) xf.fs[tid - 128] = st->fix_s[tid - 128];
   if (tid == 64) {
     double m = 0.0;
     for (int c = 0; c < 3; ++c)
@@ -591,6 +649,9 @@ __device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict_
 
 #ifndef B200_LEFT_SCAN_BATCH
 #define B200_LEFT_SCAN_BATCH 4   // candidate loads in flight per lane in the leftover batches (2: 7.60, 4: 7.56 ms)
+#endif
+#ifndef B200_FIXPOINT
+#define B200_FIXPOINT 1   // 0: fp64 sums, static hand-out only (A/B builds)
 #endif
 #ifndef B200_DUAL_TILE
 #define B200_DUAL_TILE 0
@@ -611,6 +672,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
                 const __grid_constant__ CommDev comm) {
   if (st->done) return;
   constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
+  constexpr bool FIXP = B200_FIXPOINT && !NAPX && !PLANE;   // order-independent sums + dynamic hand-out
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   IterSmem<NS>& sm = *reinterpret_cast<IterSmem<NS>*>(dyn_smem);
   __shared__ XfSmem xf;
@@ -622,6 +684,12 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   // needs the previous pose (iter > 0) and every point visited every iteration (no subsampling)
   const bool can_skip = st->iters_run > 0 && rnd <= 1;
   const float dmax = 0.1f * (float)model.h, dmin = 1e-3f * (float)model.h;
+  // Hand-out mode of this launch (every block takes the same decision from state the previous launch left).  While
+  // (nearly) all points search, a warp's share of the scan is ~9 batches of 32 searches, each as long as its slowest
+  // lane (10-60 us): with a static split the slowest warp takes 1.6x the median (tools/warp_times.py).  Then the
+  // warps draw their 32-point groups from one counter instead; the order-independent sums keep the result
+  // reproducible.  (Runs of 2 / 4 groups per draw: 8.2 / 9.8 ms per match against 7.4 -- one group it is.)
+  const bool dyn = FIXP && rnd <= 1 && (st->iters_run == 0 || st->searches_last > nd - (nd >> 4));   // > 15/16
   SmemAcc acc{&sm.acc[0][tid]};
 #pragma unroll 4
   for (int k = 0; k < NS; ++k) acc[k] = 0.0;
@@ -659,7 +727,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
     if (on) {
       nn_cache[i] = bj;
       nn_budget[i] = newbud;
-      if (bj >= 0) accumulate_pair<NAPX, PLANE>(pc, acc, i, bj, tx, ty, tz);
+      if (bj >= 0) accumulate_pair<NAPX, PLANE, FIXP>(pc, acc, i, bj, tx, ty, tz);
     }
     __syncwarp();
   };
@@ -688,7 +756,7 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
           const double d2 = EXACT ? exact_d2(model, seed, sx, sy, sz)
                                   : (double)dist32(__ldg(model.p32 + seed), (float)(sx - model.c[0]),
                                                    (float)(sy - model.c[1]), (float)(sz - model.c[2]));
-          if (d2 < maxdist2) accumulate_pair<NAPX, PLANE>(pc, acc, i, seed, tx, ty, tz);
+          if (d2 < maxdist2) accumulate_pair<NAPX, PLANE, FIXP>(pc, acc, i, seed, tx, ty, tz);
         }
       }
     }
@@ -731,9 +799,23 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
       }
   }
 #else
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t i = tile * kBlock + tid;
-    enqueue(i, stream_one(i, i < nd));
+  {
+    // one loop for both modes: static = tile b, b + grid, ... of the block (warp w takes the tile's group w);
+    // dynamic = the next group of the scan, whoever asks (the draw for the group after this one is issued before the
+    // work and read after it, so its latency is hidden)
+    const uint32_t ngroups = (nd + 31u) / 32u;
+    uint32_t g = blockIdx.x * kWarps + warp;
+    unsigned gnext = 0;
+    if (dyn) {
+      if (lane == 0) gnext = atomicAdd(stage2_counter + 3, 1u);
+      g = __shfl_sync(0xffffffffu, gnext, 0);
+    }
+    while (g < ngroups) {
+      if (dyn && lane == 0) gnext = atomicAdd(stage2_counter + 3, 1u);
+      const uint32_t i = g * 32u + lane;
+      enqueue(i, stream_one(i, i < nd));
+      g = dyn ? __shfl_sync(0xffffffffu, gnext, 0) : g + gridDim.x * kWarps;
+    }
   }
 #endif
   wrp_mark(1);
@@ -770,10 +852,19 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   for (int k = warp; k < NS; k += kWarps) {
     const double* col = &sm.acc[k][0];
     double v = 0.0;
+    if (FIXP) {
+      long long iv = 0;
 #pragma unroll
-    for (int u = 0; u < kBlock / 32; ++u) v += col[u * 32 + lane];
+      for (int u = 0; u < kBlock / 32; ++u) iv += __double_as_longlong(col[u * 32 + lane]);
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      for (int m = 16; m > 0; m >>= 1) iv += __shfl_xor_sync(0xffffffffu, iv, m);
+      v = __longlong_as_double(iv);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kBlock / 32; ++u) v += col[u * 32 + lane];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    }
     if (lane == 0) partials[(size_t)blockIdx.x * NS_MAX + k] = v;
   }
   blk_mark(2);
@@ -786,12 +877,12 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   if (tid == 0) {
     const unsigned ticket = atomicAdd(stage2_counter + 2, 1u);
     is_last = ticket == gridDim.x - 1;
-    if (is_last) stage2_counter[2] = 0;   // ready for the next launch
+    if (is_last) { stage2_counter[2] = 0; stage2_counter[3] = 0; }   // ready for the next launch
   }
   __syncthreads();
   if (is_last) {
     __threadfence();
-    solve_step(st, partials, (int)gridDim.x, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
+    solve_step(st, partials, (int)gridDim.x, FIXP, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
   }
 }
 

@@ -326,7 +326,7 @@ icp_search_kernel(GridDev model, const double4* __restrict__ dq, const double4* 
   if (is_last) {
     tl_mark(7);
     __threadfence();
-    solve_step(st, partials, nseg + (int)active_blocks, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
+    solve_step(st, partials, nseg + (int)active_blocks, false, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
   }
 }
 
