@@ -846,6 +846,7 @@ int b200icp_match(b200icp_ctx* ctx, const b200icp_scan* model, b200icp_scan* dat
     hs->fixed_point = 1;
   }
   CU_TRY(cudaMemcpyAsync(ctx->d_state.p, hs, sizeof(IterState), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemsetAsync(ctx->partials.p, 0, NS_MAX * sizeof(double), st));   // row of integer totals (fixed-point kernels)
   CU_TRY(cudaMemsetAsync(ctx->nn_cache.p, 0xFF, data->n * sizeof(int), st));  // -1: no cached neighbour
   CU_TRY(cudaMemsetAsync(ctx->nn_budget.p, 0, data->n * sizeof(float), st));
 

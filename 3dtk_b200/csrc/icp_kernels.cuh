@@ -443,6 +443,7 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
   //  round trip per block on the serial tail of the iteration -- 5.4 -> 3.5 us measured)
   constexpr int kRedGroup = 16;
   const int trips = (nblocks - warp + kWarps - 1) / kWarps;   // blocks this warp sums: warp, warp + 8, ...
+  if (!fixed)
   for (int k0 = 0; k0 < NS; k0 += 32) {
     const int k = k0 + lane;
     double v = 0.0;
@@ -454,15 +455,8 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
           const int b = warp + (j0 + u) * kWarps;
           x[u] = b < nblocks ? __ldcg(partials + (size_t)b * NS_MAX + k) : 0.0;
         }
-        if (fixed) {
-          long long iv = __double_as_longlong(v);
 #pragma unroll
-          for (int u = 0; u < kRedGroup; ++u) iv += __double_as_longlong(x[u]);
-          v = __longlong_as_double(iv);
-        } else {
-#pragma unroll
-          for (int u = 0; u < kRedGroup; ++u) v += x[u];
-        }
+        for (int u = 0; u < kRedGroup; ++u) v += x[u];
       }
       wpart[warp][k] = v;
     }
@@ -470,9 +464,10 @@ __device__ __noinline__ void solve_step(IterState* __restrict__ gst, const doubl
   __syncthreads();
   if (tid < NS) {
     if (fixed) {
-      long long iv = 0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) iv += __double_as_longlong(wpart[w][tid]);
+      // the blocks have added their integer sums into row 0 (icp_iter_kernel); read, scale back, clear for the next launch
+      unsigned long long* tot = reinterpret_cast<unsigned long long*>(const_cast<double*>(partials)) + tid;
+      const long long iv = (long long)__ldcg(tot);
+      *tot = 0ull;
       mom[tid] = (double)iv * st->fix_inv[tid];
     } else {
       mom[tid] = ((wpart[0][tid] + wpart[1][tid]) + (wpart[2][tid] + wpart[3][tid])) +
@@ -865,7 +860,10 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
 #pragma unroll
       for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     }
-    if (lane == 0) partials[(size_t)blockIdx.x * NS_MAX + k] = v;
+    // integer sums need no row per block: they are added straight into ONE row of totals (integer atomics are exact
+    // and order-independent), which the last block only has to read -- the 444-row reduction leaves the serial tail
+    if (FIXP) { if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(partials) + k, (unsigned long long)__double_as_longlong(v)); }
+    else if (lane == 0) partials[(size_t)blockIdx.x * NS_MAX + k] = v;
   }
   blk_mark(2);
   if (lane == 0 && stage2) atomicAdd(stage2_counter, stage2);
