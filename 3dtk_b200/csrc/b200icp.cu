@@ -18,6 +18,9 @@
 
 #include "common.cuh"
 #include "grid_build.cuh"
+#ifndef B200_PDL
+#define B200_PDL 1
+#endif
 #include "icp_kernels.cuh"
 #include "stream_kernels.cuh"
 #include "normals.cuh"
@@ -191,11 +194,27 @@ cudaError_t launch_iter(b200icp_ctx* ctx, int variant, const b200icp_scan* model
   const int grid = (int)std::min<uint32_t>(
       ntiles, (uint32_t)(ctx->sm_count * std::min(ctx->blocks_per_sm[variant], kMaxBlocksPerSm)));
   *grid_out = grid;
+#if B200_PDL
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, model->g, (const double4*)data->g.p64, (const double4*)data->g.nrm, nd,
+                            ctx->d_state.p, maxdist2, rnd, ctx->nn_cache.p, ctx->nn_budget.p, ctx->partials.p,
+                            ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p, ctx->stage2_log.p, comm);
+#else
   kern<<<grid, kBlock, smem, ctx->stream>>>(model->g, data->g.p64, data->g.nrm, nd, ctx->d_state.p,
                                             maxdist2, rnd, ctx->nn_cache.p, ctx->nn_budget.p, ctx->partials.p,
                                             ctx->stage2_counter.p, ctx->rms_log.p, ctx->npairs_log.p,
                                             ctx->stage2_log.p, comm);
   return cudaSuccess;
+#endif
 }
 
 int launch_iter_dispatch(b200icp_ctx* ctx, bool napx, bool plane, bool exact,

@@ -645,6 +645,9 @@ __device__ __forceinline__ void load_xf(XfSmem& xf, const IterState* __restrict_
 #ifndef B200_LEFT_SCAN_BATCH
 #define B200_LEFT_SCAN_BATCH 4   // candidate loads in flight per lane in the leftover batches (2: 7.60, 4: 7.56 ms)
 #endif
+#ifndef B200_PDL
+#define B200_PDL 1
+#endif
 #ifndef B200_FIXPOINT
 #define B200_FIXPOINT 1   // 0: fp64 sums, static hand-out only (A/B builds)
 #endif
@@ -665,6 +668,11 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
                 unsigned* __restrict__ stage2_counter, double* __restrict__ rms_log,
                 unsigned long long* __restrict__ npairs_log, unsigned* __restrict__ stage2_log,
                 const __grid_constant__ CommDev comm) {
+#if B200_PDL
+  // programmatic dependent launch: this launch may have been started while its predecessor's last block was still
+  // reducing and solving (see the trigger below); nothing of the predecessor may be read before this returns
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   if (st->done) return;
   constexpr int NS = NAPX ? (int)NS_NAPX : (int)NS_P2P;
   constexpr bool FIXP = B200_FIXPOINT && !NAPX && !PLANE;   // order-independent sums + dynamic hand-out
@@ -879,6 +887,10 @@ icp_iter_kernel(GridDev model, const double4* __restrict__ dq, const double4* __
   }
   __syncthreads();
   if (is_last) {
+#if B200_PDL
+    // every other block has exited: with this trigger the next launch's blocks are scheduled while the tail runs
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     __threadfence();
     solve_step(st, partials, (int)gridDim.x, FIXP, rms_log, npairs_log, stage2_log, stage2_counter, &sm.acc[0][0], comm);
   }
