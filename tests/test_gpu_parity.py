@@ -131,6 +131,24 @@ def test_match_point_to_point_vs_oracle(icp, ctx, algo, iteration_form):
     np.testing.assert_allclose(moved, want["xyz"], rtol=0, atol=1e-8)
 
 
+@pytest.mark.parametrize("scale,offset", [(0.01, 0.0), (1000.0, 0.0), (1.0, 5.0e4)])
+def test_match_in_other_units_and_far_from_the_origin(icp, ctx, scale, offset):
+    """The point-to-point kernel sums its pair moments as 64-bit integers with per-match power-of-two scales taken from
+    the scene's extent (order-independent sums, icp_kernels.cuh): metres instead of centimetres, a 1000x larger scene
+    and a scene 500 m away from the origin must register like the oracle, pair for pair."""
+    model, data, _ = make_pair(icp, 30000, 30000)
+    model, data = model * scale + offset, data * scale + offset
+    md, eps = 25.0 * scale, 1e-5 * scale
+    want = orclib.port_match(model, data, algo=1, max_dist=md, max_iter=30, eps=eps)
+    m, d = icp.Scan(ctx, model, max_dist_hint=md), icp.Scan(ctx, data, max_dist_hint=md)
+    got = icp.icp6D(ctx, algo=1, max_dist_match=md, max_num_iterations=30, epsilon_icp=eps).match(m, d)
+    T, _ = d.get_pose()
+    assert got["iterations"] == want["iterations"]
+    assert np.array_equal(got["npairs"], want["npairs"])
+    np.testing.assert_allclose(got["rms"], want["rms"], rtol=1e-8)
+    assert orclib.rel_frobenius(T, want["transmat"]) < 1e-8 < TOL_MATCH
+
+
 def test_match_fast_mode_within_north_star_tolerance(icp, ctx):
     model, data, _ = make_pair(icp, 60000, 50000)
     want = orclib.port_match(model, data, algo=1, max_dist=25.0, max_iter=50, eps=1e-5)
