@@ -7,10 +7,17 @@
 //                     (reference src/slam6d/scan.cc:1220-1260, searchTree.cc:92-188,
 //                     icp6Dquat.cc:57-71) and makes Scan::transformReduced (scan.cc:851-875)
 //                     disappear: the cumulative transform is applied on load.
-//   icp_solve_kernel  one tiny launch per iteration: fixed-order reduction of the per-block moments,
-//                     the 6-DoF solve (solve.h), pose composition (scan.cc:878-898) and the
-//                     convergence test of icp6D::match (icp6D.cc:266-279), all in fp64 on device.
+//                     The scan is handed out in 32-point groups, statically or -- while nearly all points
+//                     search -- dynamically from one counter; the point-to-point variants sum their
+//                     moments as 64-bit integers (order-independent: reruns stay bit-equal under any
+//                     hand-out, and the block sums are added into one row of totals with atomics).
+//   solve_step        run by the LAST block of that launch (no second launch): totals of the moments, the
+//                     6-DoF solve (solve.h; for QUAT spread over the 32 lanes of a warp,
+//                     solve_quat_warp), pose composition (scan.cc:878-898) and the convergence test of
+//                     icp6D::match (icp6D.cc:266-279), all in fp64 on device.  The next launch is
+//                     released (programmatic dependent launch) when this tail starts.
 //   nn_batch_kernel   SearchTree::getPtPairs for caller-supplied queries (API path).
+//   lum_link_kernel   lum6DEuler::covarianceEuler / lum6DQuat::covarianceQuat sums of one link.
 #pragma once
 #include <type_traits>
 #include "nn_search.cuh"
