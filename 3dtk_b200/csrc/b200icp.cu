@@ -433,7 +433,7 @@ int b200icp_scan_create_device(b200icp_ctx* ctx, const double* d_xyz, const doub
   double h_floor = std::max(max_ext * 1e-6, 1e-9);  // smallest edge whose dense table fits the cap
   while (cells_for(ext, h_floor, dims) > (double)kCellCap) h_floor *= 1.08;
   const char* env_ppc = getenv("B200ICP_TARGET_PPC");
-  const double target_ppc = env_ppc ? std::max(atof(env_ppc), 0.25) : 4.0;
+  const double target_ppc = env_ppc ? std::max(atof(env_ppc), 0.25) : 4.5;   // (sweep on the final kernels, 1M/1M: 3.5 / 4 / 4.5 / 5 / 6 -> 7.09 / 7.13 / 7.02 / 7.07 / 7.12 ms)
   DevBuf<uint32_t> counts;
   DevBuf<unsigned long long> occ_dev;
   CU_TRY(occ_dev.alloc_async(1, st));
